@@ -1,0 +1,15 @@
+"""roomslam_b200: B200-native (sm_100a) implementation of Room-SLAM's data-parallel hot path.
+
+Public surface mirrors the upstream README's `src/models/room_slam.py` and `src/models/baseline.py`:
+`RoomSLAM` (nn.Module: bi-GRU encoder + MLP decoder heads + multi-task loss) and `OccupancyHeatmapBaseline`.
+All arithmetic runs in hand-written CUDA behind the C ABI in include/roomslam_b200.h; no CPU fallback.
+"""
+from .baseline import OccupancyHeatmapBaseline  # noqa: F401
+from . import synth  # noqa: F401
+
+__all__ = ["OccupancyHeatmapBaseline", "synth"]
+try:
+    from .model import RoomSLAM  # noqa: F401
+    __all__.append("RoomSLAM")
+except ImportError:  # model.py lands with the GRU kernels
+    pass
