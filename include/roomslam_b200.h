@@ -44,6 +44,52 @@ int rs_heatmap_bin_host(const float* host_points, int64_t n_traces, int64_t seq_
                         float res, int gx, int gy, float thr2, int32_t* host_occ, int32_t* host_stat,
                         unsigned long long* host_dropped);
 
+/* ---- fp32 building blocks of the RoomSLAM model (replace torch.nn.GRU / nn.Linear / losses on the hot path) --- */
+/* Sequence buffers are addressed as element(b, t, c) = p[((b*rows + row0 + t) * ld) + c]: plain (B, T, C) tensors
+ * use rows = T, row0 = 0; the library's padded activation layout uses rows = T + 2, row0 = 1 with zero pad rows. */
+#define RS_GEMM_ACCUMULATE 1
+#define RS_GEMM_RELU 2
+/* C[m,n] = act(sum_k A[m*a_sm + k*a_sk] * B[k*b_sk + n*b_sn] + bias[n]) (+ C).  fp32 CUDA-core GEMM. */
+int rs_sgemm(const float* A, int64_t a_sm, int64_t a_sk, const float* B, int64_t b_sk, int64_t b_sn, float* C,
+             int64_t ldc, const float* bias, int M, int N, int K, int flags, void* stream);
+/* out[n] (+)= sum_m A[m*lda + n] */
+int rs_colsum_f32(const float* A, int64_t lda, int M, int N, float* out, int accumulate, void* stream);
+/* One bidirectional GRU layer, forward (torch.nn.GRU semantics, rnn.py:1221-1224; zero initial state).
+ * Either x (input size I <= 4, projection fused; w_ih [2][3H][I]) or P ([., 6H] = x W_ih^T + b_ih for both
+ * directions) feeds the layer.  w_hh_t [2][H][3H] (transposed), b_ih/b_hh [2][3H], out [., 2H], h_n [2][B][H],
+ * gates [2][B][T][4][H] (r, z, n, W_hn h + b_hn; NULL to skip saving for inference). */
+int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int64_t x_row0, int I, const float* w_ih,
+                   const float* b_ih, const float* P, int64_t p_ld, int64_t p_rows, int64_t p_row0,
+                   const float* w_hh_t, const float* b_hh, float* out, int64_t o_ld, int64_t o_rows, int64_t o_row0,
+                   float* h_n, float* gates, int B, int T, int H, void* stream);
+/* Backward through time of the same layer.  d_out [., 2H] and d_h_n [2][B][H] may be NULL (zero).  w_hh [2][3H][H].
+ * Writes dGx, dGh [., 6H]: gradients w.r.t. the input-side / hidden-side gate pre-activations. */
+int rs_gru_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows, int64_t do_row0, const float* d_h_n,
+                   const float* gates, const float* out, int64_t o_ld, int64_t o_rows, int64_t o_row0,
+                   const float* w_hh, float* dGx, float* dGh, int64_t g_ld, int64_t g_rows, int64_t g_row0, int B, int T,
+                   int H, void* stream);
+/* o = a * m element-wise over sequence buffers (m NULL: copy).  Inter-layer dropout mask (decision D4). */
+int rs_seq_mul_f32(const float* a, int64_t a_ld, int64_t a_rows, int64_t a_row0, const float* m, int64_t m_ld,
+                   int64_t m_rows, int64_t m_row0, float* o, int64_t o_ld, int64_t o_rows, int64_t o_row0, int B, int T,
+                   int C, void* stream);
+/* Decoder heads: raw [B, N*(C+6)] (columns class | pos | size | orient | valid) -> the five prediction tensors;
+ * sizes = softplus(raw) + 1e-4 (analogue src/benchmark/model.py:129). */
+int rs_heads_split_f32(const float* raw, int B, int N, int C, float* cls, float* pos, float* size, float* orient,
+                       float* valid, void* stream);
+int rs_heads_merge_bwd_f32(const float* raw, int B, int N, int C, const float* d_cls, const float* d_pos,
+                           const float* d_size, const float* d_orient, const float* d_valid, float* d_raw, void* stream);
+int rs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* Multi-task loss (README.md:122-125): weights5 is a HOST array {class, position, size, orientation, validity}.
+ * losses6 = {total, class, position, size, orientation, validity}; sums6 (double) and g_* keep what backward needs. */
+int rs_loss_fwd_f32(const float* cls, const float* pos, const float* size, const float* orient, const float* vlogit,
+                    const int64_t* t_cls, const float* t_pos, const float* t_size, const float* t_orient,
+                    const float* t_valid, int B, int N, int C, const float* weights5, double* sums6, float* losses6,
+                    float* g_cls, float* g_pos, float* g_size, float* g_orient, float* g_valid, void* stream);
+int rs_loss_bwd_f32(const double* sums6, const float* d_losses6, int B, int N, int C, const float* weights5,
+                    const float* g_cls, const float* g_pos, const float* g_size, const float* g_orient,
+                    const float* g_valid, float* d_cls, float* d_pos, float* d_size, float* d_orient, float* d_valid,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

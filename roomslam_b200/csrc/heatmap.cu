@@ -238,9 +238,9 @@ extern "C" int rs_heatmap_bin_variant(const float* points, int64_t n_traces, int
                                       unsigned long long* n_dropped, int accumulate, int variant, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
-    RS_REQUIRE(points && occ && stat && n_dropped, "rs_heatmap_bin: null pointer argument");
     RS_REQUIRE(n_traces >= 0 && seq_len >= 0 && seq_len < (1 << 30), "rs_heatmap_bin: bad shape (%lld, %lld)",
                (long long)n_traces, (long long)seq_len);
+    RS_REQUIRE((points || n_traces * seq_len == 0) && occ && stat && n_dropped, "rs_heatmap_bin: null pointer argument");
     RS_REQUIRE(gx > 0 && gy > 0 && (long long)gx * gy < (1ll << 30) && gx < (1 << 21) && gy < (1 << 21),
                "rs_heatmap_bin: bad grid %d x %d", gx, gy);
     RS_REQUIRE(res > 0.0f, "rs_heatmap_bin: resolution must be positive");
@@ -307,8 +307,9 @@ extern "C" int rs_heatmap_bin_host(const float* host_points, int64_t n_traces, i
                                    float y_min, float res, int gx, int gy, float thr2, int32_t* host_occ,
                                    int32_t* host_stat, unsigned long long* host_dropped) {
     if (rs::check_device_sm100()) return 3;
-    RS_REQUIRE(host_points && host_occ && host_stat && host_dropped, "rs_heatmap_bin_host: null pointer argument");
     RS_REQUIRE(n_traces >= 0 && seq_len >= 0, "rs_heatmap_bin_host: bad shape");
+    RS_REQUIRE((host_points || n_traces * seq_len == 0) && host_occ && host_stat && host_dropped,
+               "rs_heatmap_bin_host: null pointer argument");
     static cudaStream_t streams[2] = {nullptr, nullptr};
     static float* stage[2] = {nullptr, nullptr};
     static int32_t* d_grids = nullptr;
