@@ -34,8 +34,9 @@ int rs_device_ok(void);                /* 1 when the current CUDA device is sm_1
 int rs_heatmap_bin(const float* points, int64_t n_traces, int64_t seq_len, float x_min, float y_min, float res,
                    int gx, int gy, float thr2, int32_t* occ, int32_t* stat, unsigned long long* n_dropped,
                    int accumulate, void* stream);
-/* Same, forcing a kernel variant (0 auto, 1 TMA 16 warps x 8-point chunks, 2 TMA 8 warps x 16-point chunks,
- * 3 generic global-atomic kernel).  For tests and tuning. */
+/* Same, forcing a kernel variant: 0 auto (5 when the TMA path applies, else 3); TMA variants are
+ * warps x points-per-chunk x stages: 1 = 16x8x2, 2 = 8x16x2, 4 = 32x8x1, 5 = 24x8x1; 3 = generic global-atomic
+ * kernel (odd seq_len, unaligned pointers, grids above 40960 cells).  For tests and tuning. */
 int rs_heatmap_bin_variant(const float* points, int64_t n_traces, int64_t seq_len, float x_min, float y_min,
                            float res, int gx, int gy, float thr2, int32_t* occ, int32_t* stat,
                            unsigned long long* n_dropped, int accumulate, int variant, void* stream);

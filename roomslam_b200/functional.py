@@ -1,0 +1,301 @@
+"""autograd.Function wrappers that orchestrate the C-ABI kernels for the RoomSLAM model.
+
+Host-side mirror of what torch.nn.GRU / nn.Linear / the loss functions do in the CPU reference
+(oracle/room_slam_ref.py): same tensors in and out, but every FLOP runs in libroomslam_b200.so.
+torch is used for device memory, streams and autograd bookkeeping only.
+
+Activation layout ("padded"): every per-timestep activation lives in a (B, T+2, C) buffer whose rows 0 and T+1
+of each trace are zero.  h_{t-1} of step t is then simply "the row before" (forward direction) or "the row
+after" (reverse direction) for every t including the boundary, which lets dW_hh = sum_t dGh_t^T h_{t-1} run as
+ONE time-parallel GEMM with a one-row pointer shift.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACC, RELU = 1, 2
+LOSS_WEIGHTS = (2.0, 5.0, 5.0, 1.0, 1.0)   # class, position, size, orientation, validity (decision D9)
+_W5 = (ctypes.c_float * 5)(*LOSS_WEIGHTS)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.RoomSlamError("roomslam_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def sgemm(A, a_sm, a_sk, Bm, b_sk, b_sn, C, ldc, bias, M, N, K, flags=0):
+    _lib.call("rs_sgemm", _p(A), a_sm, a_sk, _p(Bm), b_sk, b_sn, _p(C), ldc, _p(bias), M, N, K, flags, _stream(C))
+
+
+def linear_nt(x2d: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor, flags=0):
+    """out[M,N] = x2d[M,K] @ w[N,K]^T + bias."""
+    M, K = x2d.shape
+    N = w.shape[0]
+    sgemm(x2d, x2d.stride(0), 1, w, 1, w.stride(0), out, out.stride(0), bias, M, N, K, flags)
+
+
+def matmul_nn(a2d: torch.Tensor, w: torch.Tensor, out: torch.Tensor, flags=0):
+    """out[M,N] = a2d[M,K] @ w[K,N]."""
+    M, K = a2d.shape
+    N = w.shape[1]
+    sgemm(a2d, a2d.stride(0), 1, w, w.stride(0), 1, out, out.stride(0), None, M, N, K, flags)
+
+
+def matmul_tn(a2d: torch.Tensor, b2d: torch.Tensor, out: torch.Tensor, flags=0):
+    """out[M,N] = a2d[K,M]^T @ b2d[K,N]  (weight gradients: reduction over rows)."""
+    K, M = a2d.shape
+    N = b2d.shape[1]
+    sgemm(a2d, 1, a2d.stride(0), b2d, b2d.stride(0), 1, out, out.stride(0), None, M, N, K, flags)
+
+
+def colsum(a2d: torch.Tensor, out: torch.Tensor, accumulate=False):
+    _lib.call("rs_colsum_f32", _p(a2d), a2d.stride(0), a2d.shape[0], a2d.shape[1], _p(out), int(accumulate), _stream(out))
+
+
+def padded(B: int, T: int, C: int, device, dtype=torch.float32) -> torch.Tensor:
+    buf = torch.empty(B, T + 2, C, device=device, dtype=dtype)
+    buf[:, 0].zero_()
+    buf[:, T + 1].zero_()
+    return buf
+
+
+class GRUEncoderFn(torch.autograd.Function):
+    """Bidirectional multi-layer GRU, fp32.  apply(x, mask, L, *weights) -> (out (B,T,2H), h_n (2L,B,H)).
+
+    weights per layer: w_ih, w_hh, b_ih, b_hh, w_ih_reverse, w_hh_reverse, b_ih_reverse, b_hh_reverse
+    (torch.nn.GRU order).  mask: None or (L-1, B, T, 2H) already scaled by 1/(1-p)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, num_layers, *weights):
+        _need_cuda(x, mask, *weights)
+        x = x.contiguous().float()
+        B, T, I = x.shape
+        H = weights[1].shape[1]
+        dev = x.device
+        st = _stream(x)
+        need_grad = any(ctx.needs_input_grad)
+        outs, gates_all, xs, prepped = [], [], [], []
+        h_n = torch.empty(2 * num_layers, B, H, device=dev)
+        layer_in = None
+        for l in range(num_layers):
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l: 8 * l + 8]
+            w_ih_cat = torch.cat([w_ih, w_ih_r], 0).contiguous()                # [6H, I_l]
+            w_hh_cat = torch.stack([w_hh, w_hh_r], 0).contiguous()              # [2, 3H, H]
+            w_hh_t = w_hh_cat.transpose(1, 2).contiguous()                      # [2, H, 3H]
+            b_ih_cat = torch.cat([b_ih, b_ih_r], 0).contiguous()
+            b_hh_cat = torch.cat([b_hh, b_hh_r], 0).contiguous()
+            out = padded(B, T, 2 * H, dev)
+            gates = torch.empty(2, B, T, 4, H, device=dev) if need_grad else None
+            if l == 0 and I <= 4:
+                _lib.call("rs_gru_fwd_f32", _p(x), I, T, 0, I, _p(w_ih_cat), _p(b_ih_cat), 0, 0, 0, 0, _p(w_hh_t),
+                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n[2 * l]), _p(gates), B, T, H, st)
+                xin = x
+            else:
+                if l == 0:
+                    xin = padded(B, T, I, dev)
+                    xin[:, 1:T + 1] = x
+                else:
+                    xin = layer_in
+                Il = xin.shape[-1]
+                P = torch.empty(B, T + 2, 6 * H, device=dev)
+                linear_nt(xin.view(B * (T + 2), Il), w_ih_cat, b_ih_cat, P.view(B * (T + 2), 6 * H))
+                _lib.call("rs_gru_fwd_f32", 0, 0, 0, 0, Il, 0, _p(b_ih_cat), _p(P), 6 * H, T + 2, 1, _p(w_hh_t),
+                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n[2 * l]), _p(gates), B, T, H, st)
+                del P
+            outs.append(out)
+            gates_all.append(gates)
+            xs.append(xin)
+            prepped.append((w_ih_cat, w_hh_cat))
+            if l < num_layers - 1:
+                if mask is not None:
+                    nxt = padded(B, T, 2 * H, dev)
+                    m = mask[l].contiguous()
+                    _lib.call("rs_seq_mul_f32", _p(out), 2 * H, T + 2, 1, _p(m), 2 * H, T, 0, _p(nxt), 2 * H, T + 2, 1,
+                              B, T, 2 * H, st)
+                    layer_in = nxt
+                else:
+                    layer_in = out
+        ctx.dims = (B, T, I, H, num_layers)
+        ctx.mask = mask
+        ctx.saved = (outs, gates_all, xs, prepped)
+        ctx.x_requires_grad = x.requires_grad
+        return outs[-1][:, 1:T + 1, :], h_n
+
+    @staticmethod
+    def backward(ctx, d_out, d_h_n):
+        B, T, I, H, L = ctx.dims
+        outs, gates_all, xs, prepped = ctx.saved
+        if gates_all[0] is None:
+            raise RuntimeError("GRUEncoderFn: forward ran without saving activations (no input required grad)")
+        dev = outs[0].device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        Tp = T + 2
+        M = B * Tp
+        grads: List[Optional[torch.Tensor]] = [None] * (8 * L)
+        d_h_n = d_h_n.contiguous() if d_h_n is not None else None
+        # gradient w.r.t. the current layer's output sequence: (ptr tensor, ld, rows, row0)
+        if d_out is not None:
+            d_out = d_out.contiguous()
+            cur = (d_out, 2 * H, T, 0)
+        else:
+            cur = None
+        dx = None
+        for l in range(L - 1, -1, -1):
+            w_ih_cat, w_hh_cat = prepped[l]
+            out, gates, xin = outs[l], gates_all[l], xs[l]
+            dGx = padded(B, T, 6 * H, dev)
+            dGh = padded(B, T, 6 * H, dev)
+            dhn_l = d_h_n[2 * l: 2 * l + 2].contiguous() if d_h_n is not None else None
+            _lib.call("rs_gru_bwd_f32", _p(cur[0]) if cur else 0, cur[1] if cur else 0, cur[2] if cur else 0,
+                      cur[3] if cur else 0, _p(dhn_l), _p(gates), _p(out), 2 * H, Tp, 1, _p(w_hh_cat), _p(dGx), _p(dGh),
+                      6 * H, Tp, 1, B, T, H, st)
+            dGx2, dGh2, out2 = dGx.view(M, 6 * H), dGh.view(M, 6 * H), out.view(M, 2 * H)
+            # input-side weight / bias gradients (both directions at once)
+            Il = w_ih_cat.shape[1]
+            if xin.shape[1] == T:                       # layer 0 with the fused projection: x is not padded
+                xp = padded(B, T, Il, dev)
+                xp[:, 1:T + 1] = xin
+                xin = xp
+            dW_ih = torch.empty(6 * H, Il, device=dev)
+            matmul_tn(dGx2, xin.view(M, Il), dW_ih)
+            db_ih = torch.empty(6 * H, device=dev)
+            colsum(dGx2, db_ih)
+            db_hh = torch.empty(6 * H, device=dev)
+            colsum(dGh2, db_hh)
+            # hidden-side weight gradients: pair row r of dGh with row r-1 (forward) / r+1 (reverse) of out
+            dW_hh = torch.empty(2, 3 * H, H, device=dev)
+            matmul_tn(dGh2[1:, 0:3 * H], out2[:M - 1, 0:H], dW_hh[0])
+            matmul_tn(dGh2[:M - 1, 3 * H:6 * H], out2[1:, H:2 * H], dW_hh[1])
+            grads[8 * l + 0], grads[8 * l + 4] = dW_ih[:3 * H], dW_ih[3 * H:]
+            grads[8 * l + 1], grads[8 * l + 5] = dW_hh[0], dW_hh[1]
+            grads[8 * l + 2], grads[8 * l + 6] = db_ih[:3 * H], db_ih[3 * H:]
+            grads[8 * l + 3], grads[8 * l + 7] = db_hh[:3 * H], db_hh[3 * H:]
+            if l > 0 or ctx.x_requires_grad:
+                dX = torch.empty(B, Tp, Il, device=dev)
+                matmul_nn(dGx2, w_ih_cat, dX.view(M, Il))
+                if l > 0:
+                    if ctx.mask is not None:
+                        m = ctx.mask[l - 1].contiguous()
+                        _lib.call("rs_seq_mul_f32", _p(dX), Il, Tp, 1, _p(m), Il, T, 0, _p(dX), Il, Tp, 1, B, T, Il, st)
+                    cur = (dX, Il, Tp, 1)
+                else:
+                    dx = dX[:, 1:T + 1, :]
+            del dGx, dGh
+        return (dx, None, None, *grads)
+
+
+class DecoderFn(torch.autograd.Function):
+    """MLP trunk (2 x Linear+ReLU) + five heads, fp32.
+    apply(latent, N, C, W1, b1, W2, b2, Wc, bc, Wp, bp, Ws, bs, Wo, bo, Wv, bv) -> 5 prediction tensors."""
+
+    @staticmethod
+    def forward(ctx, latent, N, C, W1, b1, W2, b2, *heads):
+        _need_cuda(latent, W1, W2, *heads)
+        latent = latent.contiguous().float()
+        B = latent.shape[0]
+        dev = latent.device
+        Wh = torch.cat(heads[0::2], 0).contiguous()      # [N*(C+6), D]
+        bh = torch.cat(heads[1::2], 0).contiguous()
+        D1, D2, NH = W1.shape[0], W2.shape[0], Wh.shape[0]
+        f1 = torch.empty(B, D1, device=dev)
+        f2 = torch.empty(B, D2, device=dev)
+        raw = torch.empty(B, NH, device=dev)
+        linear_nt(latent, W1.contiguous(), b1, f1, RELU)
+        linear_nt(f1, W2.contiguous(), b2, f2, RELU)
+        linear_nt(f2, Wh, bh, raw)
+        cls = torch.empty(B, N, C, device=dev)
+        pos = torch.empty(B, N, 2, device=dev)
+        size = torch.empty(B, N, 2, device=dev)
+        orient = torch.empty(B, N, device=dev)
+        valid = torch.empty(B, N, device=dev)
+        _lib.call("rs_heads_split_f32", _p(raw), B, N, C, _p(cls), _p(pos), _p(size), _p(orient), _p(valid), _stream(raw))
+        ctx.save_for_backward(latent, W1, W2, Wh, f1, f2, raw)
+        ctx.dims = (B, N, C)
+        ctx.head_rows = [h.shape[0] for h in heads[0::2]]
+        return cls, pos, size, orient, valid
+
+    @staticmethod
+    def backward(ctx, d_cls, d_pos, d_size, d_orient, d_valid):
+        latent, W1, W2, Wh, f1, f2, raw = ctx.saved_tensors
+        B, N, C = ctx.dims
+        dev = latent.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        c = lambda t: t.contiguous() if t is not None else None  # noqa: E731
+        d_cls, d_pos, d_size, d_orient, d_valid = c(d_cls), c(d_pos), c(d_size), c(d_orient), c(d_valid)
+        d_raw = torch.empty_like(raw)
+        _lib.call("rs_heads_merge_bwd_f32", _p(raw), B, N, C, _p(d_cls), _p(d_pos), _p(d_size), _p(d_orient),
+                  _p(d_valid), _p(d_raw), st)
+        dWh = torch.empty_like(Wh)
+        matmul_tn(d_raw, f2, dWh)
+        dbh = torch.empty(Wh.shape[0], device=dev)
+        colsum(d_raw, dbh)
+        df2 = torch.empty_like(f2)
+        matmul_nn(d_raw, Wh, df2)
+        _lib.call("rs_relu_bwd_f32", _p(df2), _p(f2), _p(df2), df2.numel(), st)
+        dW2 = torch.empty_like(W2)
+        matmul_tn(df2, f1, dW2)
+        db2 = torch.empty(W2.shape[0], device=dev)
+        colsum(df2, db2)
+        df1 = torch.empty_like(f1)
+        matmul_nn(df2, W2.contiguous(), df1)
+        _lib.call("rs_relu_bwd_f32", _p(df1), _p(f1), _p(df1), df1.numel(), st)
+        dW1 = torch.empty_like(W1)
+        matmul_tn(df1, latent, dW1)
+        db1 = torch.empty(W1.shape[0], device=dev)
+        colsum(df1, db1)
+        dlat = torch.empty_like(latent)
+        matmul_nn(df1, W1.contiguous(), dlat)
+        head_grads = []
+        r0 = 0
+        for rows in ctx.head_rows:
+            head_grads += [dWh[r0:r0 + rows], dbh[r0:r0 + rows]]
+            r0 += rows
+        return (dlat, None, None, dW1, db1, dW2, db2, *head_grads)
+
+
+class MultiTaskLossFn(torch.autograd.Function):
+    """apply(cls, pos, size, orient, valid_logits, t_cls, t_pos, t_size, t_orient, t_valid) -> losses[6]
+    = [total, class, position, size, orientation, validity] (README.md:122-125, weights D9)."""
+
+    @staticmethod
+    def forward(ctx, cls, pos, size, orient, vlogit, t_cls, t_pos, t_size, t_orient, t_valid):
+        _need_cuda(cls, pos, size, orient, vlogit, t_cls, t_pos, t_size, t_orient, t_valid)
+        B, N, C = cls.shape
+        dev = cls.device
+        f = lambda t: t.contiguous().float()  # noqa: E731
+        cls, pos, size, orient, vlogit = f(cls), f(pos), f(size), f(orient), f(vlogit)
+        t_cls = t_cls.contiguous().long()
+        t_pos, t_size, t_orient, t_valid = f(t_pos), f(t_size), f(t_orient), f(t_valid)
+        sums = torch.empty(6, dtype=torch.float64, device=dev)
+        losses = torch.empty(6, device=dev)
+        g = [torch.empty_like(t) for t in (cls, pos, size, orient, vlogit)]
+        _lib.call("rs_loss_fwd_f32", _p(cls), _p(pos), _p(size), _p(orient), _p(vlogit), _p(t_cls), _p(t_pos),
+                  _p(t_size), _p(t_orient), _p(t_valid), B, N, C, ctypes.addressof(_W5), _p(sums), _p(losses),
+                  *[_p(t) for t in g], _stream(cls))
+        ctx.save_for_backward(sums, *g)
+        ctx.dims = (B, N, C)
+        return losses
+
+    @staticmethod
+    def backward(ctx, d_losses):
+        sums, *g = ctx.saved_tensors
+        B, N, C = ctx.dims
+        d_losses = d_losses.contiguous().float()
+        d = [torch.empty_like(t) for t in g]
+        _lib.call("rs_loss_bwd_f32", _p(sums), _p(d_losses), B, N, C, ctypes.addressof(_W5), *[_p(t) for t in g],
+                  *[_p(t) for t in d], _stream(sums))
+        return (*d, None, None, None, None, None)

@@ -1,0 +1,135 @@
+"""RoomSLAM nn.Module on B200: bidirectional-GRU encoder + MLP decoder heads + multi-task loss.
+
+Drop-in for the `src/models/room_slam.py` the upstream README describes (README.md:110-125, :147-157; no code
+upstream).  Constructor, forward(), compute_loss() and state_dict() keys are identical to the
+CPU oracle (oracle/room_slam_ref.py), so `cuda_model.load_state_dict(oracle.state_dict())` is the parity harness
+and checkpoints interchange.  The arithmetic runs in libroomslam_b200.so; nothing falls back to torch ops.
+
+precision="fp32": CUDA-core kernels, parity 1e-4 relative to torch's CPU path.
+precision="bf16": tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate), parity 2e-2.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import functional as F_
+
+CLASS_NAMES = ("GROUND", "LOW", "MID", "BLOCK")    # README.md:20-23, decision D7
+LOSS_KEYS = ("total", "class", "position", "size", "orientation", "validity")
+
+
+class GRUParams(nn.Module):
+    """Parameter container with torch.nn.GRU's names, shapes, order and U(-1/sqrt(H), 1/sqrt(H)) init
+    (torch/nn/modules/rnn.py:1301), so that state_dicts interchange with the oracle's nn.GRU."""
+
+    def __init__(self, input_size: int, hidden_size: int, num_layers: int):
+        super().__init__()
+        self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
+        H = hidden_size
+        self._names = []
+        for layer in range(num_layers):
+            in_l = input_size if layer == 0 else 2 * H
+            for sfx in ("", "_reverse"):
+                for name, shape in ((f"weight_ih_l{layer}{sfx}", (3 * H, in_l)), (f"weight_hh_l{layer}{sfx}", (3 * H, H)),
+                                    (f"bias_ih_l{layer}{sfx}", (3 * H,)), (f"bias_hh_l{layer}{sfx}", (3 * H,))):
+                    self.register_parameter(name, nn.Parameter(torch.empty(*shape)))
+                    self._names.append(name)
+        stdv = 1.0 / math.sqrt(H)
+        for p in self.parameters():
+            nn.init.uniform_(p, -stdv, stdv)
+
+    def flat_weights(self):
+        return [getattr(self, n) for n in self._names]
+
+
+class Decoder(nn.Module):
+    """Parameter container for the MLP decoder (README.md:117-120; decision D6).  nn.Linear is used only to hold
+    and initialise weights; the math runs in DecoderFn."""
+
+    def __init__(self, in_features: int, hidden: int, max_objects: int, num_classes: int):
+        super().__init__()
+        self.max_objects, self.num_classes = max_objects, num_classes
+        self.trunk = nn.Sequential(nn.Linear(in_features, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU())
+        self.class_head = nn.Linear(hidden, max_objects * num_classes)
+        self.pos_head = nn.Linear(hidden, max_objects * 2)
+        self.size_head = nn.Linear(hidden, max_objects * 2)
+        self.orient_head = nn.Linear(hidden, max_objects)
+        self.valid_head = nn.Linear(hidden, max_objects)
+
+    def forward(self, latent: torch.Tensor) -> Dict[str, torch.Tensor]:
+        heads = []
+        for h in (self.class_head, self.pos_head, self.size_head, self.orient_head, self.valid_head):
+            heads += [h.weight, h.bias]
+        cls, pos, size, orient, valid = F_.DecoderFn.apply(
+            latent, self.max_objects, self.num_classes, self.trunk[0].weight, self.trunk[0].bias,
+            self.trunk[2].weight, self.trunk[2].bias, *heads)
+        return {"class_logits": cls, "positions": pos, "sizes": size, "orientations": orient, "validity_logits": valid}
+
+
+class RoomSLAM(nn.Module):
+    def __init__(self, input_size: int = 2, hidden_size: int = 128, num_layers: int = 2, max_objects: int = 10,
+                 num_classes: int = 4, dropout: float = 0.1, decoder_hidden: int = 256, precision: str = "fp32"):
+        super().__init__()
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if hidden_size % 32 or not (32 <= hidden_size <= 512):
+            raise ValueError("hidden_size must be a multiple of 32 in [32, 512]")
+        self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
+        self.max_objects, self.num_classes, self.dropout = max_objects, num_classes, dropout
+        self.precision = precision
+        self.encoder = GRUParams(input_size, hidden_size, num_layers)
+        self.decoder = Decoder(2 * hidden_size, decoder_hidden, max_objects, num_classes)
+
+    # -- dropout mask (decision D4: explicit Bernoulli mask so oracle and kernel see the same one) ----------
+    def make_dropout_mask(self, batch: int, seq_len: int, generator: Optional[torch.Generator] = None,
+                          device=None) -> Optional[torch.Tensor]:
+        if self.num_layers < 2 or self.dropout <= 0.0:
+            return None
+        keep = 1.0 - self.dropout
+        shape = (self.num_layers - 1, batch, seq_len, 2 * self.hidden_size)
+        gen_dev = generator.device if generator is not None else (device or "cpu")
+        m = (torch.rand(shape, generator=generator, device=gen_dev) < keep).to(torch.float32) / keep
+        return m.to(device) if device is not None else m
+
+    def _check_input(self, x: torch.Tensor):
+        if x.dim() != 3 or x.shape[-1] != self.input_size:
+            raise ValueError(f"expected input of shape (B, T, {self.input_size}), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise _lib.RoomSlamError("RoomSLAM runs on CUDA (sm_100a) only: move the model and inputs to the GPU; "
+                                     "there is no CPU fallback")
+
+    def encode(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None):
+        """(out (B,T,2H) of the top layer, h_n (2L,B,H)) with torch.nn.GRU semantics."""
+        self._check_input(x)
+        if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
+            dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
+        if dropout_mask is not None:
+            if dropout_mask.dim() == 3:
+                dropout_mask = dropout_mask.unsqueeze(0)
+            dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
+        fn = F_.GRUEncoderFn if self.precision == "fp32" else _bf16_encoder_fn()
+        return fn.apply(x, dropout_mask, self.num_layers, *self.encoder.flat_weights())
+
+    def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        _, h_n = self.encode(x, dropout_mask)
+        latent = torch.cat([h_n[-2], h_n[-1]], dim=-1)          # decision D5 (README.md:115)
+        return self.decoder(latent)
+
+    def compute_loss(self, pred: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        losses = F_.MultiTaskLossFn.apply(pred["class_logits"], pred["positions"], pred["sizes"], pred["orientations"],
+                                          pred["validity_logits"], target["classes"], target["positions"],
+                                          target["sizes"], target["orientations"], target["valid"])
+        return {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
+
+
+def _bf16_encoder_fn():
+    try:
+        from .functional_bf16 import GRUEncoderBF16Fn
+    except ImportError as e:  # pragma: no cover
+        raise _lib.RoomSlamError(f"bf16 tensor-core path unavailable: {e}")
+    return GRUEncoderBF16Fn

@@ -1,0 +1,129 @@
+"""GPU parity of the RoomSLAM model (fp32 mode): CUDA kernels through the C ABI vs the torch CPU oracle.
+Tolerance: 1e-4 relative (BASELINE.json north_star), measured as max|a-b| / max(|b|, floor)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_golden
+from oracle.room_slam_ref import RoomSLAM as RefRoomSLAM
+from roomslam_b200 import RoomSLAM, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+LOSS_KEYS = ("total", "class", "position", "size", "orientation", "validity")
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+def to_cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def run_pair(name):
+    ref, x, tgt, mask = make_golden.build_case(name)
+    B, T, H, L, N, seed, use_mask = make_golden.GRU_CASES[name]
+    dev = RoomSLAM(hidden_size=H, num_layers=L, max_objects=N, dropout=ref.dropout).cuda()
+    dev.load_state_dict(ref.state_dict())
+    dev.train(ref.training)
+    return ref, dev, x, tgt, mask
+
+
+@pytest.mark.parametrize("name", list(make_golden.GRU_CASES))
+def test_forward_loss_backward_match_oracle_and_golden(golden_gru, name):
+    ref, dev, x, tgt, mask = run_pair(name)
+    enc_ref, hn_ref = ref.encode(x, mask)
+    pred_ref = ref(x, mask)
+    loss_ref = ref.compute_loss(pred_ref, tgt)
+    loss_ref["total"].backward()
+
+    xm = mask.cuda() if mask is not None else None
+    enc_dev, hn_dev = dev.encode(x.cuda(), xm)
+    pred_dev = dev(x.cuda(), xm)
+    loss_dev = dev.compute_loss(pred_dev, to_cuda(tgt))
+    loss_dev["total"].backward()
+
+    # hidden states
+    assert rel_err(enc_dev, enc_ref) < RTOL and rel_err(hn_dev, hn_ref) < RTOL
+    assert rel_err(enc_dev, torch.from_numpy(golden_gru[f"{name}_enc_out"])) < RTOL
+    assert rel_err(hn_dev, torch.from_numpy(golden_gru[f"{name}_h_n"])) < RTOL
+    # predictions and losses
+    for k in pred_ref:
+        assert rel_err(pred_dev[k], pred_ref[k]) < RTOL, k
+        assert rel_err(pred_dev[k], torch.from_numpy(golden_gru[f"{name}_pred_{k}"])) < RTOL, k
+    got = np.array([loss_dev[k].item() for k in LOSS_KEYS])
+    want = np.array([loss_ref[k].item() for k in LOSS_KEYS])
+    assert np.allclose(got, want, rtol=RTOL, atol=1e-7)
+    assert np.allclose(got, golden_gru[f"{name}_losses"], rtol=RTOL, atol=1e-7)
+    # every parameter gradient
+    ref_grads = dict(ref.named_parameters())
+    for pn, p in dev.named_parameters():
+        assert p.grad is not None, pn
+        assert rel_err(p.grad, ref_grads[pn].grad) < RTOL, pn
+        d = p.grad.detach().double().cpu().reshape(-1)
+        g = golden_gru[f"{name}_grad_{pn}"]
+        assert abs(d.norm().item() - g[2]) <= RTOL * max(g[2], 1e-6), pn
+
+
+def test_c1_shape_fp32():
+    """BASELINE config 1: B=32, T=500, H=128, 2 layers, N=10 (fwd + loss + bwd)."""
+    torch.manual_seed(0)
+    ref = RefRoomSLAM(dropout=0.0).eval()
+    dev = RoomSLAM(dropout=0.0).cuda().eval()
+    dev.load_state_dict(ref.state_dict())
+    x, tgt = synth.make_sample(32, 500, 10, seed=0)
+    loss_ref = ref.compute_loss(ref(x), tgt)
+    loss_ref["total"].backward()
+    loss_dev = dev.compute_loss(dev(x.cuda()), to_cuda(tgt))
+    loss_dev["total"].backward()
+    for k in LOSS_KEYS:
+        assert abs(loss_dev[k].item() - loss_ref[k].item()) <= RTOL * max(abs(loss_ref[k].item()), 1e-6), k
+    ref_grads = dict(ref.named_parameters())
+    for pn, p in dev.named_parameters():
+        assert rel_err(p.grad, ref_grads[pn].grad) < RTOL, pn
+
+
+def test_real_traces_forward(real_traces):
+    torch.manual_seed(3)
+    ref = RefRoomSLAM(dropout=0.0).eval()
+    dev = RoomSLAM(dropout=0.0).cuda().eval()
+    dev.load_state_dict(ref.state_dict())
+    x = torch.from_numpy(real_traces["windows"])
+    with torch.no_grad():
+        a, b = ref(x), dev(x.cuda())
+    for k in a:
+        assert rel_err(b[k], a[k]) < RTOL, k
+
+
+def test_large_batch_tiles_and_loss_components_backward():
+    """B above the small-batch threshold (4 traces per thread row) and backward through single loss components."""
+    torch.manual_seed(1)
+    ref = RefRoomSLAM(dropout=0.0, hidden_size=64).eval()
+    dev = RoomSLAM(dropout=0.0, hidden_size=64).cuda().eval()
+    dev.load_state_dict(ref.state_dict())
+    x, tgt = synth.make_sample(301, 24, 10, seed=5)
+    for key in ("class", "size", "validity"):
+        ref.zero_grad(); dev.zero_grad()
+        ref.compute_loss(ref(x), tgt)[key].backward()
+        dev.compute_loss(dev(x.cuda()), to_cuda(tgt))[key].backward()
+        ref_grads = dict(ref.named_parameters())
+        for pn, p in dev.named_parameters():
+            rg = ref_grads[pn].grad
+            if rg is None or rg.abs().max() == 0:
+                assert p.grad is None or p.grad.abs().max() == 0, (key, pn)
+            else:
+                assert rel_err(p.grad, rg) < RTOL, (key, pn)
+
+
+def test_state_dict_interchange_and_errors():
+    ref = RefRoomSLAM()
+    dev = RoomSLAM()
+    assert list(ref.state_dict().keys()) == list(dev.state_dict().keys())
+    ref.load_state_dict(dev.state_dict())
+    dev.cuda()
+    with pytest.raises(ValueError):
+        dev(torch.zeros(2, 5, 3, device="cuda"))
+    with pytest.raises(RuntimeError):
+        dev(torch.zeros(2, 5, 2))      # CPU tensor: no fallback
