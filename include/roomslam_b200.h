@@ -91,6 +91,18 @@ int rs_loss_bwd_f32(const double* sums6, const float* d_losses6, int B, int N, i
                     const float* g_valid, float* d_cls, float* d_pos, float* d_size, float* d_orient, float* d_valid,
                     void* stream);
 
+/* ---- bf16 tensor-core GEMMs (tcgen05 + TMEM accumulators, TMA-fed): the time-parallel work of the bf16 mode ---- */
+/* C[M,N] (bf16, ldc) = A[M,K] (bf16, lda) . B[N,K]^T (bf16, ldb) + bias[N] (fp32, optional).  K % 64 == 0, N % 128 == 0,
+ * leading dimensions in elements and multiples of 8.  Input projection P = X W_ih^T + b_ih and dX = dG W_ih. */
+int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
+                    int64_t M, int N, int K, void* stream);
+/* C[M,N] (fp32, ldc) += A[:, a_col0:a_col0+M]^T . B[:, b_col0:b_col0+N], reduction over `rows` row pairs
+ * (row r + a_row_shift of A with row r + b_row_shift of B; rows outside a matrix count as zero).  M, N % 128 == 0.
+ * Weight gradients dW_ih = dGx^T X and dW_hh = dGh^T H_prev (one-row shift between the operands). */
+int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift, const void* B,
+                        int64_t ldb, int64_t b_rows, int b_col0, int b_row_shift, float* C, int64_t ldc, int M, int N,
+                        int64_t rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
