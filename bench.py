@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark contract:  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Headline metric (BASELINE.json): training traces/s of the RoomSLAM bi-GRU (seq 500, H 128, 2 layers, N=10 objects)
+at batch 8192 per GPU, plus the occupancy-heatmap binning throughput in Gpoints/s (1M traces x 500 points, 0.05 m grid).
+One "step" = forward + multi-task loss + backward (+ NCCL gradient all-reduce for N > 1) + clip + AdamW on one
+synthetic batch.  Weak scaling: the per-GPU batch is fixed, the global batch grows with N.
+
+Prints ONE JSON line (rank 0).  `value` is measured with the batch already resident in HBM; `e2e` repeats the
+measurement through the public API with HOST (pinned) inputs: host->device copies and the device->host read of the
+loss sit inside the timed region.  `--impl reference` times the CPU reference implementation (the torch / C oracle,
+all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SEQ_LEN, HIDDEN, LAYERS, MAX_OBJECTS = 500, 128, 2, 10
+TRAIN_BATCH = 8192                     # per GPU (BASELINE config 3)
+HEATMAP_TRACES = 1_000_000             # per GPU (BASELINE config 2)
+METRIC = "train traces/sec (seq500, H128) at 1/2/4/8 B200; heatmap Gpoints/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def gru_flops_per_trace(T=SEQ_LEN, H=HIDDEN, L=LAYERS, I=2):
+    macs = sum(3 * H * (I if l == 0 else 2 * H) + 3 * H * H for l in range(L))
+    fwd = 2.0 * 2 * T * macs
+    dec = 2.0 * (2 * H * 256 + 256 * 256 + 256 * MAX_OBJECTS * 10)
+    return 3.0 * (fwd + dec)           # fwd + dgrad + wgrad
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle on the box's host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_train_baseline(steps: int, warmup: int, sample_batch: int = 32):
+    from oracle.room_slam_ref import RoomSLAM as Ref
+    from roomslam_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = Ref(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=0.0).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    x, tgt = synth.make_sample(sample_batch, SEQ_LEN, MAX_OBJECTS, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = model.compute_loss(model(x), tgt)["total"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": sample_batch / sec, "unit": "traces/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_batch} traces x {SEQ_LEN} steps per step, fp32 torch {torch.__version__} CPU oracle "
+                      f"(fwd+loss+bwd+clip+AdamW), {steps} timed steps", "ms_per_step": sec * 1e3}
+
+
+def cpu_heatmap_baseline(reps: int = 3, sample_traces: int = 40_000):
+    import numpy as np
+    from oracle import heatmap_ref_c
+    from roomslam_b200 import synth
+    cores = os.cpu_count() or 1
+    pts = synth.make_traces(sample_traces, SEQ_LEN, seed=0).numpy()
+    thr2 = np.float32((0.1 * 0.1) ** 2)
+    heatmap_ref_c.bin_points(pts[:1000], 0, 0, 0.05, 200, 200, thr2)
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        heatmap_ref_c.bin_points(pts, 0, 0, 0.05, 200, 200, thr2, n_threads=0)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": sample_traces * SEQ_LEN / best / 1e9, "unit": "Gpoints/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_traces} traces x {SEQ_LEN} points, C restatement (oracle/heatmap_ref.c), OpenMP all cores, "
+                      f"best of {reps}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    cb = cpu_train_baseline(max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    hb = cpu_heatmap_baseline()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "traces/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, precision="fp32"),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "traces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "heatmap": {"value": hb["value"], "unit": "Gpoints/s", "cpu_baseline": hb,
+                    "e2e": {"value": hb["value"], "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, precision):
+    return {"workload": f"RoomSLAM bi-GRU H={HIDDEN} L={LAYERS} seq_len={SEQ_LEN} N={MAX_OBJECTS}, fwd+loss+bwd+clip+AdamW, "
+                        f"batch {args.batch}/GPU (global {args.batch * args.gpus}); heatmap: {args.heatmap_traces} traces x "
+                        f"{SEQ_LEN} points/GPU, 10 m x 10 m room, 0.05 m grid",
+            "global_batch": args.batch * args.gpus, "seq_len": SEQ_LEN, "hidden": HIDDEN, "layers": LAYERS,
+            "precision": precision, "parallelism": f"dp{args.gpus}",
+            "l2": "inputs larger than L2 (train activations are GBs per step; heatmap input 4 GB vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.proc, self.path = None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.count(",") >= 8]
+            sm = [float(r[1]) for r in rows]
+            loaded = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")})
+            out = {"sm_mhz": statistics.median(loaded) if loaded else None,
+                   "sm_max_mhz": float(rows[0][2]) if rows else None, "reasons": reasons, "samples": len(rows),
+                   "power_w_max": max(float(r[3]) for r in rows) if rows else None}
+        except Exception as e:  # pragma: no cover
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def timed(fn, steps, warmup, dist_on):
+    """W untimed + K timed calls of fn(); CUDA events, barrier + synchronize on both sides, max over ranks."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if dist_on:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from roomslam_b200 import RoomSLAM, OccupancyHeatmapBaseline, synth, _lib
+    from roomslam_b200 import functional as F_
+    from roomslam_b200.train_utils import FlatParams, GradReducer, FusedAdamW
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: roomslam_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    args.gpus = world
+    pk = peaks()
+    lib = _lib.load()
+    precision = args.precision
+    if precision == "auto":
+        try:
+            import roomslam_b200.functional_bf16  # noqa: F401
+            precision = "bf16"
+        except ImportError:
+            precision = "fp32"
+
+    # ---- training step -------------------------------------------------------------------------------------
+    torch.manual_seed(0)
+    model = RoomSLAM(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=0.0, precision=precision).cuda()
+    model.train()
+    flat = FlatParams(model)
+    reducer = GradReducer(flat)
+    opt = FusedAdamW(flat, lr=1e-3, max_grad_norm=1.0)
+    B = args.batch
+    x_host, tgt_host = synth.make_sample(B, SEQ_LEN, MAX_OBJECTS, seed=rank)
+    x_host = x_host.pin_memory()
+    tgt_host = {k: v.pin_memory() for k, v in tgt_host.items()}
+    x_dev = x_host.cuda()
+    tgt_dev = {k: v.cuda() for k, v in tgt_host.items()}
+    loss_host = torch.zeros(6).pin_memory()
+
+    def step(x, tgt):
+        flat.zero_grad()
+        reducer.prepare()
+        losses = model.compute_loss(model(x), tgt)
+        losses["total"].backward()
+        reducer.finish()
+        opt.step(grad_scale=1.0 / world)
+        return losses["total"]
+
+    def step_resident():
+        step(x_dev, tgt_dev)
+
+    def step_e2e():
+        x = x_host.to("cuda", non_blocking=True)
+        tgt = {k: v.to("cuda", non_blocking=True) for k, v in tgt_host.items()}
+        loss = step(x, tgt)
+        loss_host[0:1].copy_(loss.detach().reshape(1), non_blocking=False)     # device -> host read of the loss
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.rs_launch_count()
+    ms_train = timed(step_resident, args.steps, args.warmup, dist_on)
+    launches_train = (lib.rs_launch_count() - n0) // (args.steps + args.warmup) * args.steps
+    ms_train_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), dist_on)
+    h2d_train = x_host.numel() * 4 + sum(v.numel() * v.element_size() for v in tgt_host.values())
+    final_loss = float(loss_host[0])
+
+    # per-kernel timing of one extra step (CUDA events on the launch stream) for the roofline object
+    prof = F_.enable_kernel_timing(True) if hasattr(F_, "enable_kernel_timing") else None
+    if prof is not None:
+        step_resident()
+        torch.cuda.synchronize()
+        kernel_ms = F_.collect_kernel_timing()
+        F_.enable_kernel_timing(False)
+    else:
+        kernel_ms = {}
+    del x_dev, tgt_dev
+    torch.cuda.empty_cache()
+
+    # ---- heatmap -------------------------------------------------------------------------------------------
+    hm = OccupancyHeatmapBaseline()
+    n_tr = args.heatmap_traces
+    pts = synth.make_traces(n_tr, SEQ_LEN, seed=1000 + rank, device="cuda")
+    occ = torch.empty(hm.gy, hm.gx, dtype=torch.int32, device="cuda")
+    stat = torch.empty_like(occ)
+    dropped = torch.empty(1, dtype=torch.int64, device="cuda")
+    packed = torch.empty(2 * hm.gx * hm.gy, dtype=torch.int32, device="cuda")
+
+    def heat_resident():
+        hm.bin_into(pts, occ, stat, dropped)
+        if dist_on:       # sharded per trace: exact int32 sum of the two grids
+            packed[: hm.gx * hm.gy].copy_(occ.reshape(-1))
+            packed[hm.gx * hm.gy:].copy_(stat.reshape(-1))
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+
+    n1 = lib.rs_launch_count()
+    ms_heat = timed(heat_resident, args.steps, args.warmup, dist_on)
+    launches_heat = (lib.rs_launch_count() - n1) // (args.steps + args.warmup) * args.steps
+    # the binning kernel alone (events around the single launch, same stream)
+    ms_kernel = timed(lambda: hm.bin_into(pts, occ, stat, dropped), args.steps, 1, False)
+    conserved = int(occ.sum().item()) + int(dropped.item()) == n_tr * SEQ_LEN
+    pts_host = torch.empty(n_tr, SEQ_LEN, 2, dtype=torch.float32).pin_memory()
+    pts_host.copy_(pts)
+    del pts
+    torch.cuda.empty_cache()
+
+    def heat_e2e():
+        o, s, _ = hm.bin(pts_host)               # CPU tensor in -> rs_heatmap_bin_host -> CPU tensors out
+        if dist_on:
+            both = torch.cat([o.reshape(-1), s.reshape(-1)]).cuda()
+            dist.all_reduce(both, op=dist.ReduceOp.SUM)
+            both.cpu()
+
+    ms_heat_e2e = timed(heat_e2e, max(1, min(args.steps, 3)), 1, dist_on)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        traces_s = B * world / (ms_train / 1e3)
+        flops = gru_flops_per_trace()
+        line = {
+            "metric": METRIC, "value": traces_s, "unit": "traces/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args, precision),
+            "e2e": {"value": B * world / (ms_train_e2e / 1e3), "unit": "traces/s", "h2d_bytes_per_step": h2d_train,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_train_e2e},
+            "gpu_launches": int(launches_train + launches_heat),
+            "clocks": clocks, "final_loss": final_loss,
+            "train": {"algorithmic_gflop_per_trace": flops / 1e9,
+                      "achieved_tflops_per_gpu": flops * B / (ms_train / 1e3) / 1e12,
+                      "frac_of_sustained_bf16_peak": flops * B / (ms_train / 1e3) / 1e12 / pk["tflops_sustained"],
+                      "kernel_ms": kernel_ms},
+            "heatmap": {
+                "value": n_tr * SEQ_LEN * world / (ms_heat / 1e3) / 1e9, "unit": "Gpoints/s", "ms_per_step": ms_heat,
+                "points_per_gpu": n_tr * SEQ_LEN, "conservation_check": bool(conserved),
+                "e2e": {"value": n_tr * SEQ_LEN * world / (ms_heat_e2e / 1e3) / 1e9, "unit": "Gpoints/s",
+                        "h2d_bytes_per_step": n_tr * SEQ_LEN * 8, "d2h_bytes_per_step": 2 * hm.gx * hm.gy * 4 + 8,
+                        "ms_per_step": ms_heat_e2e},
+                "roofline": {"bound": "hbm", "achieved": n_tr * SEQ_LEN * 8 / (ms_kernel / 1e3) / 1e9, "peak": pk["hbm_gbs"],
+                             "unit": "GB/s", "frac": n_tr * SEQ_LEN * 8 / (ms_kernel / 1e3) / 1e9 / pk["hbm_gbs"],
+                             "traffic": None, "kernel": "heatmap_tma_kernel", "kernel_ms": ms_kernel,
+                             "algorithmic_bytes_per_point": 8, "peak_source": pk["source"]},
+            },
+        }
+        line["roofline"] = train_roofline(kernel_ms, B, pk, precision) or line["heatmap"]["roofline"]
+        if world == 1:
+            cb = cpu_train_baseline(2, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["heatmap"]["cpu_baseline"] = cpu_heatmap_baseline()
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def train_roofline(kernel_ms, B, pk, precision):
+    """Roofline object for the kernel with the largest share of the training step."""
+    if not kernel_ms:
+        return None
+    name, (ms, calls, flops) = max(kernel_ms.items(), key=lambda kv: kv[1][0])
+    if flops <= 0 or ms <= 0:
+        return None
+    ach = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": ach / pk["tflops_sustained"], "traffic": None, "kernel": name, "kernel_ms": ms, "launches": calls,
+            "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="traces per GPU")
+    ap.add_argument("--heatmap-traces", type=int, default=HEATMAP_TRACES, help="traces per GPU")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

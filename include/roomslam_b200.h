@@ -26,6 +26,7 @@ extern "C" {
 const char* rs_last_error(void);       /* thread-local message of the last failing call */
 int rs_abi_version(void);              /* bumped on any signature change */
 int rs_device_ok(void);                /* 1 when the current CUDA device is sm_100 (B200), else 0 */
+int64_t rs_launch_count(void);         /* kernels launched by this library so far (process-wide) */
 
 /* ---- occupancy heatmap + stationary time (replaces README.md:15,163-164 `src/models/baseline.py`) ------- */
 /* points: float32 [n_traces, seq_len, 2].  occ, stat: int32 [gy, gx].  n_dropped: one uint64.
@@ -102,6 +103,12 @@ int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void
 int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift, const void* B,
                         int64_t ldb, int64_t b_rows, int b_col0, int b_row_shift, float* C, int64_t ldc, int M, int N,
                         int64_t rows, void* stream);
+
+/* ---- optimizer: global-norm clipping + AdamW over one flat fp32 buffer (upstream train.py:220, :440-444) ------- */
+/* g is first scaled by grad_scale (1/world_size after a sum all-reduce), then clipped to max_norm (<= 0: off). */
+int rs_adamw_step_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float grad_scale, float max_norm, double* sumsq_scratch,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[str, List[str]]]:
     text = open(path).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const char\*|int|void)\s+(rs_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(const char\*|int64_t|int|void)\s+(rs_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         types = []
         if args and args != "void":
@@ -54,7 +54,7 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     for name, (ret, types) in parse_header().items():
         fn = getattr(lib, name)  # AttributeError if the header declares something the library lacks
-        fn.restype = ctypes.c_char_p if ret == "const char*" else (None if ret == "void" else ctypes.c_int)
+        fn.restype = {"const char*": ctypes.c_char_p, "void": None, "int64_t": ctypes.c_int64}.get(ret, ctypes.c_int)
         fn.argtypes = [ctypes.c_void_p if t == "ptr" else _C2CT[t] for t in types]
     _lib = lib
     return lib

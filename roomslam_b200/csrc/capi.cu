@@ -8,6 +8,9 @@
 namespace rs {
 
 static thread_local char g_error[1024] = "";
+static unsigned long long g_launches = 0;
+
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -78,4 +81,5 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
 
 extern "C" const char* rs_last_error(void) { return rs::g_error; }
 extern "C" int rs_abi_version(void) { return 1; }
+extern "C" int64_t rs_launch_count(void) { return (int64_t)__atomic_load_n(&rs::g_launches, __ATOMIC_RELAXED); }
 extern "C" int rs_device_ok(void) { return rs::check_device_sm100() == 0 ? 1 : 0; }

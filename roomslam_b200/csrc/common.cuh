@@ -13,6 +13,7 @@ namespace rs {
 // ---- C-ABI error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_device_sm100();  // 0 when the current device is sm_100; sets the error otherwise
+void count_launch(int n = 1);  // bookkeeping for rs_launch_count(): kernels launched by this library
 
 #define RS_CUDA_OK(expr)                                                                    \
     do {                                                                                    \

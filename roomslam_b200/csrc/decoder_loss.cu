@@ -176,6 +176,7 @@ extern "C" int rs_heads_split_f32(const float* raw, int B, int N, int C, float* 
     RS_REQUIRE(raw && cls && pos && size && orient && valid, "rs_heads_split_f32: null pointer");
     if (B == 0) return 0;
     heads_split_kernel<<<blocks_for((long long)B * N * (C + 6)), 256, 0, stream>>>(raw, B, N, C, cls, pos, size, orient, valid);
+    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -189,6 +190,7 @@ extern "C" int rs_heads_merge_bwd_f32(const float* raw, int B, int N, int C, con
     if (B == 0) return 0;
     heads_merge_kernel<<<blocks_for((long long)B * N * (C + 6)), 256, 0, stream>>>(raw, B, N, C, d_cls, d_pos, d_size,
                                                                                   d_orient, d_valid, d_raw);
+                                                                                  rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -199,6 +201,7 @@ extern "C" int rs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64
     RS_REQUIRE(dy && y && dx, "rs_relu_bwd_f32: null pointer");
     if (n == 0) return 0;
     relu_bwd_kernel<<<blocks_for(n), 256, 0, stream>>>(dy, y, dx, n);
+    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -220,8 +223,10 @@ extern "C" int rs_loss_fwd_f32(const float* cls, const float* pos, const float* 
                                                               reinterpret_cast<const long long*>(t_cls), t_pos, t_size,
                                                               t_orient, t_valid, slots, C, sums6, g_cls, g_pos, g_size,
                                                               g_orient, g_valid);
+                                                              rs::count_launch();
     loss_finalize_kernel<<<1, 32, 0, stream>>>(sums6, slots, losses6, weights5[0], weights5[1], weights5[2], weights5[3],
                                                weights5[4]);
+                                               rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -239,6 +244,7 @@ extern "C" int rs_loss_bwd_f32(const double* sums6, const float* d_losses6, int 
     loss_bwd_kernel<<<blocks_for(slots), 256, 0, stream>>>(sums6, d_losses6, slots, C, weights5[0], weights5[1],
                                                            weights5[2], weights5[3], weights5[4], g_cls, g_pos, g_size,
                                                            g_orient, g_valid, d_cls, d_pos, d_size, d_orient, d_valid);
+                                                           rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -262,6 +262,7 @@ extern "C" int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_
     long long tiles = (long long)p.m_tiles * p.n_tiles;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);
+    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -306,6 +307,7 @@ extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, i
     const int total = out_tiles * splits;
     int grid = total < num_sms() ? total : num_sms();
     gemm_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, ta, p);
+    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }

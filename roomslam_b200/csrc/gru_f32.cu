@@ -266,6 +266,7 @@ extern "C" int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int6
         else RS_LAUNCH_FWD(RR, false, 1024);                                                                     \
     } while (0)
     if (big) RS_PICK_FWD(4); else RS_PICK_FWD(1);
+    rs::count_launch();
 #undef RS_PICK_FWD
 #undef RS_LAUNCH_FWD
     RS_CUDA_OK(cudaGetLastError());
@@ -303,6 +304,7 @@ extern "C" int rs_gru_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows
         else RS_LAUNCH_BWD(RR, false, 1024);                                                                    \
     } while (0)
     if (big) RS_PICK_BWD(4); else RS_PICK_BWD(1);
+    rs::count_launch();
 #undef RS_PICK_BWD
 #undef RS_LAUNCH_BWD
     RS_CUDA_OK(cudaGetLastError());
@@ -321,6 +323,7 @@ extern "C" int rs_seq_mul_f32(const float* a, int64_t a_ld, int64_t a_rows, int6
     if (blocks > 148 * 8) blocks = 148 * 8;
     seq_mul_kernel<<<(int)blocks, 256, 0, stream>>>(mk(a, a_ld, a_rows, a_row0), mk(m, m_ld, m_rows, m_row0),
                                                     mk(o, o_ld, o_rows, o_row0), B, T, C);
+                                                    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -281,6 +281,7 @@ int launch_tma(const float* points, long long n_traces, int seq_len, const BinPa
     if (grid > g_num_sms) grid = g_num_sms;
     kern<<<grid, kWarps * 32, smem, stream>>>(tmap, P, n_traces, seq_len, static_cast<int>(n_tiles), hist_bytes, occ,
                                               stat, dropped);
+                                              rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -342,6 +343,7 @@ extern "C" int rs_heatmap_bin_variant(const float* points, int64_t n_traces, int
             if (blocks > 148ll * 16) blocks = 148ll * 16;
             heatmap_generic_kernel<<<(int)blocks, 256, 0, stream>>>(points, n_points, (int)seq_len, P, occ, stat,
                                                                     n_dropped);
+                                                                    rs::count_launch();
             RS_CUDA_OK(cudaGetLastError());
             return 0;
         }

@@ -127,6 +127,7 @@ extern "C" int rs_sgemm(const float* A, int64_t a_sm, int64_t a_sk, const float*
         }
     }
     sgemm_kernel<<<grid, 256, 0, stream>>>(A, a_sm, a_sk, B, b_sk, b_sn, C, ldc, bias, M, N, K, k_per_split, flags);
+    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -141,6 +142,7 @@ extern "C" int rs_colsum_f32(const float* A, int64_t lda, int M, int N, float* o
     if (slabs > 128) slabs = 128;
     const int rows_per_block = (M + slabs - 1) / slabs;
     colsum_kernel<<<dim3((N + 31) / 32, slabs), dim3(32, 8), 0, stream>>>(A, lda, M, N, rows_per_block, out);
+    rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -23,6 +23,49 @@ LOSS_WEIGHTS = (2.0, 5.0, 5.0, 1.0, 1.0)   # class, position, size, orientation,
 _W5 = (ctypes.c_float * 5)(*LOSS_WEIGHTS)
 
 
+# ---- optional per-kernel timing (CUDA events on the launch stream; used by bench.py for the roofline object) ----
+_KT = {"on": False, "events": []}
+
+
+class ktime:
+    """with ktime("kernel name", algorithmic_flops): <one C-ABI call>"""
+
+    def __init__(self, name: str, flops: float = 0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _KT["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _KT["on"]:
+            self.e1.record()
+            _KT["events"].append((self.name, self.e0, self.e1, self.flops))
+        return False
+
+
+def enable_kernel_timing(flag: bool):
+    _KT["on"] = bool(flag)
+    _KT["events"] = []
+    return True
+
+
+def collect_kernel_timing():
+    """{kernel: [total ms, launches, total algorithmic flops]} since enable_kernel_timing(True)."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, fl in _KT["events"]:
+        rec = out.setdefault(name, [0.0, 0, 0.0])
+        rec[0] += e0.elapsed_time(e1)
+        rec[1] += 1
+        rec[2] += fl
+    _KT["events"] = []
+    return out
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -73,129 +116,123 @@ def padded(B: int, T: int, C: int, device, dtype=torch.float32) -> torch.Tensor:
     return buf
 
 
-class GRUEncoderFn(torch.autograd.Function):
-    """Bidirectional multi-layer GRU, fp32.  apply(x, mask, L, *weights) -> (out (B,T,2H), h_n (2L,B,H)).
+class GRULayerFn(torch.autograd.Function):
+    """ONE bidirectional GRU layer, fp32 kernels.
 
-    weights per layer: w_ih, w_hh, b_ih, b_hh, w_ih_reverse, w_hh_reverse, b_ih_reverse, b_hh_reverse
-    (torch.nn.GRU order).  mask: None or (L-1, B, T, 2H) already scaled by 1/(1-p)."""
+    apply(xin, padded_in, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        -> (out_padded (B, T+2, 2H), h_n (2, B, H))
+    xin : padded_in False: the traces (B, T, I);  True: the padded output (B, T+2, I) of the layer below.
+    mask: None or (B, T, I) dropout keep-mask (scaled by 1/(1-p)) applied to xin (decision D4).
+    One Function per layer, so a layer's weight gradients are final (and can be all-reduced) while the
+    backward-through-time of the layer below is still running."""
 
     @staticmethod
-    def forward(ctx, x, mask, num_layers, *weights):
-        _need_cuda(x, mask, *weights)
-        x = x.contiguous().float()
-        B, T, I = x.shape
-        H = weights[1].shape[1]
-        dev = x.device
-        st = _stream(x)
+    def forward(ctx, xin, padded_in, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        _need_cuda(xin, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        xin = xin.contiguous().float()
+        ctx.padded_in_orig = bool(padded_in)
+        B, Il = xin.shape[0], xin.shape[2]
+        T = xin.shape[1] - 2 if padded_in else xin.shape[1]
+        H = w_hh.shape[1]
+        dev = xin.device
+        st = _stream(xin)
         need_grad = any(ctx.needs_input_grad)
-        outs, gates_all, xs, prepped = [], [], [], []
-        h_n = torch.empty(2 * num_layers, B, H, device=dev)
-        layer_in = None
-        for l in range(num_layers):
-            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = weights[8 * l: 8 * l + 8]
-            w_ih_cat = torch.cat([w_ih, w_ih_r], 0).contiguous()                # [6H, I_l]
-            w_hh_cat = torch.stack([w_hh, w_hh_r], 0).contiguous()              # [2, 3H, H]
-            w_hh_t = w_hh_cat.transpose(1, 2).contiguous()                      # [2, H, 3H]
-            b_ih_cat = torch.cat([b_ih, b_ih_r], 0).contiguous()
-            b_hh_cat = torch.cat([b_hh, b_hh_r], 0).contiguous()
-            out = padded(B, T, 2 * H, dev)
-            gates = torch.empty(2, B, T, 4, H, device=dev) if need_grad else None
-            if l == 0 and I <= 4:
-                _lib.call("rs_gru_fwd_f32", _p(x), I, T, 0, I, _p(w_ih_cat), _p(b_ih_cat), 0, 0, 0, 0, _p(w_hh_t),
-                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n[2 * l]), _p(gates), B, T, H, st)
-                xin = x
-            else:
-                if l == 0:
-                    xin = padded(B, T, I, dev)
-                    xin[:, 1:T + 1] = x
-                else:
-                    xin = layer_in
-                Il = xin.shape[-1]
-                P = torch.empty(B, T + 2, 6 * H, device=dev)
+        w_ih_cat = torch.cat([w_ih, w_ih_r], 0).contiguous()                # [6H, I_l]
+        w_hh_cat = torch.stack([w_hh, w_hh_r], 0).contiguous()              # [2, 3H, H]
+        w_hh_t = w_hh_cat.transpose(1, 2).contiguous()                      # [2, H, 3H]
+        b_ih_cat = torch.cat([b_ih, b_ih_r], 0).contiguous()
+        b_hh_cat = torch.cat([b_hh, b_hh_r], 0).contiguous()
+        out = padded(B, T, 2 * H, dev)
+        h_n = torch.empty(2, B, H, device=dev)
+        gates = torch.empty(2, B, T, 4, H, device=dev) if need_grad else None
+        if mask is not None:
+            xm = padded(B, T, Il, dev)
+            m = mask.contiguous().float()
+            _lib.call("rs_seq_mul_f32", _p(xin), Il, xin.shape[1], 1 if padded_in else 0, _p(m), Il, T, 0, _p(xm), Il,
+                      T + 2, 1, B, T, Il, st)
+            xin, padded_in = xm, True
+        rec_flops = 2.0 * B * T * 2 * 3 * H * H
+        if Il <= 4:
+            with ktime("gru_fwd_f32_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
+                _lib.call("rs_gru_fwd_f32", _p(xin), Il, xin.shape[1], 1 if padded_in else 0, Il, _p(w_ih_cat),
+                          _p(b_ih_cat), 0, 0, 0, 0, _p(w_hh_t), _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n),
+                          _p(gates), B, T, H, st)
+        else:
+            if not padded_in:
+                xp = padded(B, T, Il, dev)
+                xp[:, 1:T + 1] = xin
+                xin, padded_in = xp, True
+            P = torch.empty(B, T + 2, 6 * H, device=dev)
+            with ktime("sgemm_kernel(projection)", 2.0 * B * (T + 2) * 6 * H * Il):
                 linear_nt(xin.view(B * (T + 2), Il), w_ih_cat, b_ih_cat, P.view(B * (T + 2), 6 * H))
+            with ktime("gru_fwd_f32_kernel", rec_flops):
                 _lib.call("rs_gru_fwd_f32", 0, 0, 0, 0, Il, 0, _p(b_ih_cat), _p(P), 6 * H, T + 2, 1, _p(w_hh_t),
-                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n[2 * l]), _p(gates), B, T, H, st)
-                del P
-            outs.append(out)
-            gates_all.append(gates)
-            xs.append(xin)
-            prepped.append((w_ih_cat, w_hh_cat))
-            if l < num_layers - 1:
-                if mask is not None:
-                    nxt = padded(B, T, 2 * H, dev)
-                    m = mask[l].contiguous()
-                    _lib.call("rs_seq_mul_f32", _p(out), 2 * H, T + 2, 1, _p(m), 2 * H, T, 0, _p(nxt), 2 * H, T + 2, 1,
-                              B, T, 2 * H, st)
-                    layer_in = nxt
-                else:
-                    layer_in = out
-        ctx.dims = (B, T, I, H, num_layers)
+                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n), _p(gates), B, T, H, st)
+            del P
+        ctx.dims = (B, T, Il, H)
         ctx.mask = mask
-        ctx.saved = (outs, gates_all, xs, prepped)
-        ctx.x_requires_grad = x.requires_grad
-        return outs[-1][:, 1:T + 1, :], h_n
+        ctx.saved = (out, gates, xin, padded_in, w_ih_cat, w_hh_cat)
+        return out, h_n
 
     @staticmethod
     def backward(ctx, d_out, d_h_n):
-        B, T, I, H, L = ctx.dims
-        outs, gates_all, xs, prepped = ctx.saved
-        if gates_all[0] is None:
-            raise RuntimeError("GRUEncoderFn: forward ran without saving activations (no input required grad)")
-        dev = outs[0].device
+        B, T, Il, H = ctx.dims
+        out, gates, xin, padded_in, w_ih_cat, w_hh_cat = ctx.saved
+        if gates is None:
+            raise RuntimeError("GRULayerFn: forward ran without saving activations (nothing required grad)")
+        dev = out.device
         st = torch.cuda.current_stream(dev).cuda_stream
         Tp = T + 2
         M = B * Tp
-        grads: List[Optional[torch.Tensor]] = [None] * (8 * L)
-        d_h_n = d_h_n.contiguous() if d_h_n is not None else None
-        # gradient w.r.t. the current layer's output sequence: (ptr tensor, ld, rows, row0)
-        if d_out is not None:
-            d_out = d_out.contiguous()
-            cur = (d_out, 2 * H, T, 0)
-        else:
-            cur = None
-        dx = None
-        for l in range(L - 1, -1, -1):
-            w_ih_cat, w_hh_cat = prepped[l]
-            out, gates, xin = outs[l], gates_all[l], xs[l]
-            dGx = padded(B, T, 6 * H, dev)
-            dGh = padded(B, T, 6 * H, dev)
-            dhn_l = d_h_n[2 * l: 2 * l + 2].contiguous() if d_h_n is not None else None
-            _lib.call("rs_gru_bwd_f32", _p(cur[0]) if cur else 0, cur[1] if cur else 0, cur[2] if cur else 0,
-                      cur[3] if cur else 0, _p(dhn_l), _p(gates), _p(out), 2 * H, Tp, 1, _p(w_hh_cat), _p(dGx), _p(dGh),
-                      6 * H, Tp, 1, B, T, H, st)
-            dGx2, dGh2, out2 = dGx.view(M, 6 * H), dGh.view(M, 6 * H), out.view(M, 2 * H)
-            # input-side weight / bias gradients (both directions at once)
-            Il = w_ih_cat.shape[1]
-            if xin.shape[1] == T:                       # layer 0 with the fused projection: x is not padded
-                xp = padded(B, T, Il, dev)
-                xp[:, 1:T + 1] = xin
-                xin = xp
-            dW_ih = torch.empty(6 * H, Il, device=dev)
-            matmul_tn(dGx2, xin.view(M, Il), dW_ih)
-            db_ih = torch.empty(6 * H, device=dev)
-            colsum(dGx2, db_ih)
-            db_hh = torch.empty(6 * H, device=dev)
-            colsum(dGh2, db_hh)
-            # hidden-side weight gradients: pair row r of dGh with row r-1 (forward) / r+1 (reverse) of out
-            dW_hh = torch.empty(2, 3 * H, H, device=dev)
+        d_out = d_out.contiguous().float() if d_out is not None else None          # padded (B, T+2, 2H)
+        d_h_n = d_h_n.contiguous().float() if d_h_n is not None else None
+        dGx = padded(B, T, 6 * H, dev)
+        dGh = padded(B, T, 6 * H, dev)
+        with ktime("gru_bwd_f32_kernel", 2.0 * B * T * 2 * 3 * H * H):
+            _lib.call("rs_gru_bwd_f32", _p(d_out), 2 * H, Tp, 1, _p(d_h_n), _p(gates), _p(out), 2 * H, Tp, 1,
+                      _p(w_hh_cat), _p(dGx), _p(dGh), 6 * H, Tp, 1, B, T, H, st)
+        dGx2, dGh2, out2 = dGx.view(M, 6 * H), dGh.view(M, 6 * H), out.view(M, 2 * H)
+        if not padded_in:                                # layer 0 with the fused projection: x is not padded
+            xp = padded(B, T, Il, dev)
+            xp[:, 1:T + 1] = xin
+            xin = xp
+        dW_ih = torch.empty(6 * H, Il, device=dev)
+        with ktime("sgemm_kernel(wgrad)", 2.0 * M * 6 * H * Il):
+            matmul_tn(dGx2, xin.view(M, Il), dW_ih)      # both directions at once
+        db_ih = torch.empty(6 * H, device=dev)
+        colsum(dGx2, db_ih)
+        db_hh = torch.empty(6 * H, device=dev)
+        colsum(dGh2, db_hh)
+        # hidden-side weight gradients: pair row r of dGh with row r-1 (forward) / r+1 (reverse) of out;
+        # the zero pad rows make the boundary steps (h_prev = 0) come out right
+        dW_hh = torch.empty(2, 3 * H, H, device=dev)
+        with ktime("sgemm_kernel(wgrad)", 2.0 * M * 6 * H * H):
             matmul_tn(dGh2[1:, 0:3 * H], out2[:M - 1, 0:H], dW_hh[0])
             matmul_tn(dGh2[:M - 1, 3 * H:6 * H], out2[1:, H:2 * H], dW_hh[1])
-            grads[8 * l + 0], grads[8 * l + 4] = dW_ih[:3 * H], dW_ih[3 * H:]
-            grads[8 * l + 1], grads[8 * l + 5] = dW_hh[0], dW_hh[1]
-            grads[8 * l + 2], grads[8 * l + 6] = db_ih[:3 * H], db_ih[3 * H:]
-            grads[8 * l + 3], grads[8 * l + 7] = db_hh[:3 * H], db_hh[3 * H:]
-            if l > 0 or ctx.x_requires_grad:
-                dX = torch.empty(B, Tp, Il, device=dev)
-                matmul_nn(dGx2, w_ih_cat, dX.view(M, Il))
-                if l > 0:
-                    if ctx.mask is not None:
-                        m = ctx.mask[l - 1].contiguous()
-                        _lib.call("rs_seq_mul_f32", _p(dX), Il, Tp, 1, _p(m), Il, T, 0, _p(dX), Il, Tp, 1, B, T, Il, st)
-                    cur = (dX, Il, Tp, 1)
-                else:
-                    dx = dX[:, 1:T + 1, :]
-            del dGx, dGh
-        return (dx, None, None, *grads)
+        d_xin = None
+        if ctx.needs_input_grad[0]:
+            dX = torch.empty(B, Tp, Il, device=dev)
+            with ktime("sgemm_kernel(dgrad)", 2.0 * M * 6 * H * Il):
+                matmul_nn(dGx2, w_ih_cat, dX.view(M, Il))    # pad rows of dGx are zero -> pad rows of dX are zero
+            if ctx.mask is not None:
+                m = ctx.mask.contiguous().float()
+                _lib.call("rs_seq_mul_f32", _p(dX), Il, Tp, 1, _p(m), Il, T, 0, _p(dX), Il, Tp, 1, B, T, Il, st)
+            d_xin = dX if ctx.padded_in_orig else dX[:, 1:T + 1, :]
+        return (d_xin, None, None, dW_ih[:3 * H], dW_hh[0], db_ih[:3 * H], db_hh[:3 * H],
+                dW_ih[3 * H:], dW_hh[1], db_ih[3 * H:], db_hh[3 * H:])
+
+
+def gru_encoder(x, mask, num_layers, weights, layer_fn=None):
+    """Stack of bidirectional layers -> (out (B,T,2H) of the top layer, h_n (2L,B,H)), torch.nn.GRU semantics."""
+    layer_fn = layer_fn or GRULayerFn
+    T = x.shape[1]
+    cur, padded_in, h_all = x, False, []
+    for l in range(num_layers):
+        m = mask[l - 1] if (mask is not None and l > 0) else None
+        cur, h_n = layer_fn.apply(cur, padded_in, m, *weights[8 * l: 8 * l + 8])
+        padded_in = True
+        h_all.append(h_n)
+    return cur[:, 1:T + 1, :], (torch.cat(h_all, 0) if num_layers > 1 else h_all[0])
 
 
 class DecoderFn(torch.autograd.Function):

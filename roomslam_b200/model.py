@@ -112,8 +112,8 @@ class RoomSLAM(nn.Module):
             if dropout_mask.dim() == 3:
                 dropout_mask = dropout_mask.unsqueeze(0)
             dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
-        fn = F_.GRUEncoderFn if self.precision == "fp32" else _bf16_encoder_fn()
-        return fn.apply(x, dropout_mask, self.num_layers, *self.encoder.flat_weights())
+        layer_fn = F_.GRULayerFn if self.precision == "fp32" else _bf16_layer_fn()
+        return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn)
 
     def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         _, h_n = self.encode(x, dropout_mask)
@@ -127,9 +127,9 @@ class RoomSLAM(nn.Module):
         return {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
 
 
-def _bf16_encoder_fn():
+def _bf16_layer_fn():
     try:
-        from .functional_bf16 import GRUEncoderBF16Fn
+        from .functional_bf16 import GRULayerBF16Fn
     except ImportError as e:  # pragma: no cover
         raise _lib.RoomSlamError(f"bf16 tensor-core path unavailable: {e}")
-    return GRUEncoderBF16Fn
+    return GRULayerBF16Fn
