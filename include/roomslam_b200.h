@@ -110,6 +110,21 @@ int rs_adamw_step_f32(float* p, const float* g, float* m, float* v, int64_t n, f
                       float eps, float weight_decay, int step, float grad_scale, float max_norm, double* sumsq_scratch,
                       void* stream);
 
+/* ---- bf16 mode: GEMMs over the TILE-MAJOR activation layout ----------------------------------------------------
+ * A per-timestep activation with C columns is stored as blocks (trace tile of 128, time row t' in [0, T+2)), each
+ * block = [C/8][128][8] bf16 (C*256 contiguous bytes); rows t' = 0 and T+1 are zero padding (h before the first /
+ * after the last step).  csrc/gemm_blk.cu explains why (1-D bulk copies, no-swizzle tcgen05 operands, coalesced
+ * per-thread access in the recurrence kernels). */
+/* For every block m < n_blocks: C_blk[:, c_chunk0*8 + n*128 ...] = A_blk[:, K blocks] . W^T + bias, K block kb =
+ * the 64 columns starting at chunk a_kchunk[kb] (HOST array); W is pre-tiled [n_tiles][k_blocks][8][128][8] bf16. */
+int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W, int n_tiles, void* C,
+                   int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks, void* stream);
+/* C[c_row0[mt] + i, j] (fp32, ldc) += sum over blocks (tile, t' = 1..T) of A_blk[:, (a_mchunk[mt])*8 + i] *
+ * B_blk'[:, b_chunk0*8 + j] with B_blk' = the block b_shift time rows away; n_cols % 16 == 0.  HOST arrays. */
+int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles, const void* B,
+                       int64_t b_cols, int b_chunk0, int n_cols, int b_shift, float* C, int64_t ldc, int tiles, int T,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,6 +212,24 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// No-swizzle ("interleaved") descriptors: the operand is stored as 8-row x 16-byte core matrices (128 contiguous
+// bytes each).  K-major: lbo = bytes between the two 16-byte K chunks of one K=16 step, sbo = bytes between
+// 8-row groups along M/N.  MN-major: lbo = bytes between 8-row groups along K, sbo = bytes between 16-byte chunks
+// along M/N.  This is the layout of the library's tile-major activations: [chunk][128 rows][8 bf16].
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+// 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP).  bytes % 16 == 0, 16-byte aligned.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 // Instruction descriptor for kind::f16 with bf16 A/B, fp32 accumulate.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (1u << 4)                 // D format: F32

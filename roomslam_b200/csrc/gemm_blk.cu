@@ -1,0 +1,345 @@
+// bf16 tensor-core GEMMs over the library's TILE-MAJOR activation layout (bf16 mode).
+//
+// Tile-major layout of a per-timestep activation with C columns: blocks indexed by (trace tile of 128, time row t'),
+// each block = [C/8 chunks][128 traces][8 bf16] = C*256 contiguous bytes.  Every block (and every run of chunks in
+// it) is ONE contiguous piece, so operands move with 1-D bulk copies (cp.async.bulk, mbarrier completion) and land in
+// shared memory already in tcgen05's no-swizzle core-matrix form (8 rows x 16 bytes = 128 contiguous bytes):
+//   as a K-major  operand (rows = traces,  K = columns): lbo = 2048 (next 16-byte K chunk), sbo = 128
+//   as an MN-major operand (M/N = columns, K = traces ): lbo = 128 (next 8 traces),        sbo = 2048
+// and the recurrence kernels read / write the same blocks with perfectly coalesced 16-byte accesses per thread.
+//
+//   blk_gemm_nt : per block m:  C_blk[:, n] = A_blk[:, kchunks] . W[n, :]^T + bias      (bf16 out, direct stores)
+//                 -> input projection P = X W_ih^T + b  and  dX = dG W_ih
+//   blk_gemm_tn : C[M, N] += sum over blocks  A_blk[:, mchunks]^T . B_blk'[:, nchunks]   (fp32 out, split over blocks)
+//                 -> dW_ih, dW_hh (block of dG at t' paired with the block of h at t' -/+ 1), bias gradients (ones column)
+//
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = tcgen05.mma issuer (one lane), warps 2..5 = TMEM epilogue.
+#include "common.cuh"
+#include "../../include/roomslam_b200.h"
+
+namespace {
+
+constexpr int CHUNK_BYTES = 2048;          // one 16-byte column chunk of a 128-trace block
+constexpr int PIECE_BYTES = 8 * CHUNK_BYTES;   // 64 columns x 128 traces = 16 KB
+constexpr int NT_STAGES = 4;
+constexpr int NT_MAX_KB = 12;
+constexpr int NUM_THREADS = 192;
+
+struct NtParams {
+    const uint8_t* A;  long long a_block_bytes;  int a_kchunk[NT_MAX_KB];   // chunk offset of each 64-column K block
+    const uint8_t* W;                                                        // [n_tiles][k_blocks][8][128][8] bf16
+    uint8_t* C;        long long c_block_bytes;  int c_chunk0;
+    const float* bias;
+    int n_blocks, n_tiles, k_blocks;
+};
+
+template <bool kResident>
+__global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* a_res = smem;                                        // 4 x 16 KB (resident A block, K <= 256)
+    uint8_t* stages = smem + 4 * PIECE_BYTES;                     // NT_STAGES x (A piece | W piece)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NT_STAGES * 2 * PIECE_BYTES);
+    uint64_t* full_bar = bars;                       // [NT_STAGES]
+    uint64_t* empty_bar = bars + NT_STAGES;          // [NT_STAGES]
+    uint64_t* acc_full = bars + 2 * NT_STAGES;       // [2]
+    uint64_t* acc_empty = bars + 2 * NT_STAGES + 2;  // [2]
+    uint64_t* a_full = bars + 2 * NT_STAGES + 4;     // resident A landed
+    uint64_t* a_empty = bars + 2 * NT_STAGES + 5;    // MMAs of the block retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NT_STAGES + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < NT_STAGES; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { rs::mbar_init(&acc_full[s], 1); rs::mbar_init(&acc_empty[s], 4); }
+        rs::mbar_init(a_full, 1);
+        rs::mbar_init(a_empty, 1);
+        rs::fence_mbar_init();
+    }
+    if (warp == 1) rs::tmem_alloc<256>(tmem_slot);
+    rs::tc_fence_before();
+    __syncthreads();
+    rs::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, a_phase = 0;
+            for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
+                const uint8_t* ablk = p.A + (long long)m * p.a_block_bytes;
+                if (kResident) {
+                    rs::mbar_wait(a_empty, a_phase ^ 1);
+                    a_phase ^= 1;
+                    rs::mbar_expect_tx(a_full, p.k_blocks * PIECE_BYTES);
+                    for (int kb = 0; kb < p.k_blocks; ++kb)
+                        rs::bulk_load(a_res + kb * PIECE_BYTES, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES, a_full);
+                }
+                for (int n = 0; n < p.n_tiles; ++n) {
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        rs::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = stages + stage * 2 * PIECE_BYTES;
+                        rs::mbar_expect_tx(&full_bar[stage], kResident ? PIECE_BYTES : 2 * PIECE_BYTES);
+                        if (!kResident)
+                            rs::bulk_load(sa, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES, &full_bar[stage]);
+                        rs::bulk_load(sa + PIECE_BYTES, p.W + ((long long)n * p.k_blocks + kb) * PIECE_BYTES, PIECE_BYTES,
+                                      &full_bar[stage]);
+                        if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = rs::umma_idesc_bf16(128, 128, 0, 0);
+        int stage = 0; uint32_t phase = 0, a_phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
+            if (kResident) { rs::mbar_wait(a_full, a_phase); a_phase ^= 1; rs::tc_fence_after(); }
+            for (int n = 0; n < p.n_tiles; ++n) {
+                rs::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                rs::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * 128;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    rs::mbar_wait(&full_bar[stage], phase);
+                    rs::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t ss = rs::smem_u32(stages + stage * 2 * PIECE_BYTES);
+                        const uint32_t sa = kResident ? rs::smem_u32(a_res + kb * PIECE_BYTES) : ss;
+                        const uint32_t sb = ss + PIECE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = rs::umma_desc_noswz(sa + k * 2 * CHUNK_BYTES, CHUNK_BYTES, 128);
+                            const uint64_t db = rs::umma_desc_noswz(sb + k * 2 * CHUNK_BYTES, CHUNK_BYTES, 128);
+                            rs::tc_mma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+                        }
+                        rs::tc_commit(&empty_bar[stage]);
+                        if (kb == p.k_blocks - 1) {
+                            rs::tc_commit(&acc_full[acc]);
+                            if (kResident && n == p.n_tiles - 1) rs::tc_commit(a_empty);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3, row = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
+            uint8_t* cblk = p.C + (long long)m * p.c_block_bytes + row * 16;
+            for (int n = 0; n < p.n_tiles; ++n) {
+                rs::mbar_wait(&acc_full[acc], acc_phase);
+                rs::tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t r[32];
+                    rs::tmem_ld_32x32b_x32(taddr + c0, r);
+                    rs::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float v0 = __uint_as_float(r[8 * j + 2 * e]), v1 = __uint_as_float(r[8 * j + 2 * e + 1]);
+                            if (p.bias) {
+                                v0 += __ldg(&p.bias[n * 128 + c0 + 8 * j + 2 * e]);
+                                v1 += __ldg(&p.bias[n * 128 + c0 + 8 * j + 2 * e + 1]);
+                            }
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        const int chunk = p.c_chunk0 + n * 16 + c0 / 8 + j;
+                        *reinterpret_cast<uint4*>(cblk + (long long)chunk * CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                rs::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) rs::mbar_arrive(&acc_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    rs::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) rs::tmem_dealloc<256>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TN_MAX_MT = 8;
+struct TnParams {
+    const uint8_t* A;  long long a_block_bytes;  int a_mchunk[TN_MAX_MT];  int c_row0[TN_MAX_MT];
+    const uint8_t* B;  long long b_block_bytes;  int b_chunk0;  int n_cols;  int b_shift;   // B block = A block + b_shift
+    float* C;  long long ldc;
+    int m_tiles, tiles, T, Tp;          // logical blocks: (tile, t' = 1..T)
+    int splits, blocks_per_split;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_tn_kernel(const TnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int b_bytes = p.n_cols * 256;
+    const int stage_bytes = 2 * PIECE_BYTES + b_bytes;            // A: 16 chunks (32 KB) | B: n_cols/8 chunks
+    uint8_t* stages = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+    uint64_t* full_bar = bars;        // [2]
+    uint64_t* empty_bar = bars + 2;   // [2]
+    uint64_t* acc_full = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 2; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], 1); }
+        rs::mbar_init(acc_full, 1);
+        rs::fence_mbar_init();
+    }
+    if (warp == 1) rs::tmem_alloc<256>(tmem_slot);
+    rs::tc_fence_before();
+    __syncthreads();
+    rs::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_blocks = p.tiles * p.T;
+    const int items = p.m_tiles * p.splits;
+    int stage = 0; uint32_t phase = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int mt = item % p.m_tiles, split = item / p.m_tiles;
+        const int i0 = split * p.blocks_per_split;
+        const int i1 = min(total_blocks, i0 + p.blocks_per_split);
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int i = i0; i < i1; ++i) {
+                    const long long blk = (long long)(i / p.T) * p.Tp + 1 + (i % p.T);
+                    rs::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = stages + stage * stage_bytes;
+                    rs::mbar_expect_tx(&full_bar[stage], 2 * PIECE_BYTES + b_bytes);
+                    rs::bulk_load(sa, p.A + blk * p.a_block_bytes + (long long)p.a_mchunk[mt] * CHUNK_BYTES, 2 * PIECE_BYTES,
+                                  &full_bar[stage]);
+                    rs::bulk_load(sa + 2 * PIECE_BYTES, p.B + (blk + p.b_shift) * p.b_block_bytes + (long long)p.b_chunk0 * CHUNK_BYTES,
+                                  b_bytes, &full_bar[stage]);
+                    if (++stage == 2) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t idesc = rs::umma_idesc_bf16(128, p.n_cols, 1, 1);
+            for (int i = i0; i < i1; ++i) {
+                rs::mbar_wait(&full_bar[stage], phase);
+                rs::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = rs::smem_u32(stages + stage * stage_bytes);
+                    const uint32_t sb = sa + 2 * PIECE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {       // 128 traces = 8 K-steps of 16
+                        const uint64_t da = rs::umma_desc_noswz(sa + k * 256, 128, CHUNK_BYTES);
+                        const uint64_t db = rs::umma_desc_noswz(sb + k * 256, 128, CHUNK_BYTES);
+                        rs::tc_mma_bf16(tmem_base, da, db, idesc, (i != i0) || (k != 0));
+                    }
+                    rs::tc_commit(&empty_bar[stage]);
+                    if (i == i1 - 1) rs::tc_commit(acc_full);
+                }
+                __syncwarp();
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        } else if (i1 > i0) {
+            const int q = warp & 3, row = q * 32 + lane;
+            rs::mbar_wait(acc_full, acc_phase);
+            rs::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+            float* crow = p.C + (long long)(p.c_row0[mt] + row) * p.ldc;
+            for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
+                uint32_t r[16];
+                rs::tmem_ld_32x32b_x16(taddr + c0, r);
+                rs::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(crow + c0 + j, __uint_as_float(r[j]));
+            }
+            rs::tc_fence_before();
+        }
+        if (i1 > i0) acc_phase ^= 1;
+        // the single accumulator is reused by the next item: everyone meets here (rarely more than one item per CTA)
+        __syncthreads();
+        rs::tc_fence_after();
+    }
+    rs::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) rs::tmem_dealloc<256>(tmem_base);
+}
+
+int g_sms = 0;
+int num_sms() {
+    if (g_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sms;
+}
+
+}  // namespace
+
+extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W,
+                              int n_tiles, void* C, int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks,
+                              void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(A && W && C && a_kchunk, "rs_blk_gemm_nt: null pointer");
+    RS_REQUIRE(k_blocks >= 1 && k_blocks <= NT_MAX_KB && n_tiles >= 1, "rs_blk_gemm_nt: 1 <= k_blocks <= %d", NT_MAX_KB);
+    RS_REQUIRE(a_cols % 8 == 0 && c_cols % 8 == 0 && n_blocks < (1ll << 31), "rs_blk_gemm_nt: bad shape");
+    if (n_blocks == 0) return 0;
+    NtParams p = {};
+    p.A = static_cast<const uint8_t*>(A); p.a_block_bytes = a_cols * 256;
+    for (int i = 0; i < k_blocks; ++i) {
+        RS_REQUIRE(a_kchunk[i] >= 0 && (a_kchunk[i] + 8) * 8 <= a_cols, "rs_blk_gemm_nt: K block %d outside the A block", i);
+        p.a_kchunk[i] = a_kchunk[i];
+    }
+    RS_REQUIRE((c_chunk0 + n_tiles * 16) * 8 <= c_cols, "rs_blk_gemm_nt: output columns outside the C block");
+    p.W = static_cast<const uint8_t*>(W);
+    p.C = static_cast<uint8_t*>(C); p.c_block_bytes = c_cols * 256; p.c_chunk0 = c_chunk0;
+    p.bias = bias; p.n_blocks = (int)n_blocks; p.n_tiles = n_tiles; p.k_blocks = k_blocks;
+    const int smem = 4 * PIECE_BYTES + NT_STAGES * 2 * PIECE_BYTES + 256;
+    const int grid = (int)(n_blocks < num_sms() ? n_blocks : num_sms());
+    if (k_blocks <= 4) {
+        RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        blk_gemm_nt_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
+        rs::count_launch();
+    } else {
+        RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        blk_gemm_nt_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+        rs::count_launch();
+    }
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles,
+                                  const void* B, int64_t b_cols, int b_chunk0, int n_cols, int b_shift, float* C,
+                                  int64_t ldc, int tiles, int T, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(A && B && C && a_mchunk && c_row0, "rs_blk_gemm_tn_acc: null pointer");
+    RS_REQUIRE(m_tiles >= 1 && m_tiles <= TN_MAX_MT, "rs_blk_gemm_tn_acc: 1 <= m_tiles <= %d", TN_MAX_MT);
+    RS_REQUIRE(n_cols >= 16 && n_cols <= 256 && n_cols % 16 == 0, "rs_blk_gemm_tn_acc: n_cols must be a multiple of 16 in [16,256]");
+    RS_REQUIRE(b_shift >= -1 && b_shift <= 1 && tiles >= 0 && T >= 0, "rs_blk_gemm_tn_acc: bad arguments");
+    RS_REQUIRE((b_chunk0 * 8 + n_cols) <= b_cols && a_cols % 8 == 0 && b_cols % 8 == 0, "rs_blk_gemm_tn_acc: B columns outside the block");
+    const long long total = (long long)tiles * T;
+    if (total == 0) return 0;
+    RS_REQUIRE(total < (1ll << 31), "rs_blk_gemm_tn_acc: too many blocks");
+    TnParams p = {};
+    p.A = static_cast<const uint8_t*>(A); p.a_block_bytes = a_cols * 256;
+    for (int i = 0; i < m_tiles; ++i) {
+        RS_REQUIRE(a_mchunk[i] >= 0 && (a_mchunk[i] + 16) * 8 <= a_cols, "rs_blk_gemm_tn_acc: M tile %d outside the A block", i);
+        p.a_mchunk[i] = a_mchunk[i]; p.c_row0[i] = c_row0[i];
+    }
+    p.B = static_cast<const uint8_t*>(B); p.b_block_bytes = b_cols * 256; p.b_chunk0 = b_chunk0; p.n_cols = n_cols; p.b_shift = b_shift;
+    p.C = C; p.ldc = ldc; p.m_tiles = m_tiles; p.tiles = tiles; p.T = T; p.Tp = T + 2;
+    int splits = num_sms() / m_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > total) splits = (int)total;
+    p.blocks_per_split = (int)((total + splits - 1) / splits);
+    p.splits = (int)((total + p.blocks_per_split - 1) / p.blocks_per_split);
+    const int smem = 2 * (2 * PIECE_BYTES + n_cols * 256) + 256;
+    RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int items = p.m_tiles * p.splits;
+    blk_gemm_tn_kernel<<<items < num_sms() ? items : num_sms(), NUM_THREADS, smem, stream>>>(p);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
