@@ -120,10 +120,21 @@ int rs_adamw_step_f32(float* p, const float* g, float* m, float* v, int64_t n, f
 int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W, int n_tiles, void* C,
                    int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks, void* stream);
 /* C[c_row0[mt] + i, j] (fp32, ldc) += sum over blocks (tile, t' = 1..T) of A_blk[:, (a_mchunk[mt])*8 + i] *
- * B_blk'[:, b_chunk0*8 + j] with B_blk' = the block b_shift time rows away; n_cols % 16 == 0.  HOST arrays. */
+ * B_blk'[:, b_chunk0*8 + j] with B_blk' = the block b_shift time rows away (b_broadcast != 0: B is ONE block used
+ * for every (tile, t'), e.g. a column of ones for bias gradients); n_cols % 16 == 0.  HOST arrays. */
 int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles, const void* B,
-                       int64_t b_cols, int b_chunk0, int n_cols, int b_shift, float* C, int64_t ldc, int tiles, int T,
-                       void* stream);
+                       int64_t b_cols, int b_chunk0, int n_cols, int b_shift, int b_broadcast, float* C, int64_t ldc,
+                       int tiles, int T, void* stream);
+/* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
+/* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 3) fp32 + wx_packed [2][3H][4] = (w_ih row, bias);
+ * deeper layers: P tile-major (6H columns, bias folded in).  Whh [2][16][384][8] bf16, b_hn [2][H], out tile-major
+ * (2H columns, zero pad rows), gates [tiles][T][2][64][128][8] bf16 (NULL for inference), h_n [2][B][H] fp32. */
+int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, const void* P, int64_t p_cols, const void* Whh,
+                    const float* b_hn, void* out, void* gates, float* h_n, int B, int T, void* stream);
+/* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
+ * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
+int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
+                    int B, int T, void* stream);
 
 #ifdef __cplusplus
 }

@@ -310,8 +310,8 @@ extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk
 }
 
 extern "C" int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles,
-                                  const void* B, int64_t b_cols, int b_chunk0, int n_cols, int b_shift, float* C,
-                                  int64_t ldc, int tiles, int T, void* stream_) {
+                                  const void* B, int64_t b_cols, int b_chunk0, int n_cols, int b_shift, int b_broadcast,
+                                  float* C, int64_t ldc, int tiles, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     RS_REQUIRE(A && B && C && a_mchunk && c_row0, "rs_blk_gemm_tn_acc: null pointer");
@@ -328,7 +328,7 @@ extern "C" int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mc
         RS_REQUIRE(a_mchunk[i] >= 0 && (a_mchunk[i] + 16) * 8 <= a_cols, "rs_blk_gemm_tn_acc: M tile %d outside the A block", i);
         p.a_mchunk[i] = a_mchunk[i]; p.c_row0[i] = c_row0[i];
     }
-    p.B = static_cast<const uint8_t*>(B); p.b_block_bytes = b_cols * 256; p.b_chunk0 = b_chunk0; p.n_cols = n_cols; p.b_shift = b_shift;
+    p.B = static_cast<const uint8_t*>(B); p.b_block_bytes = b_broadcast ? 0 : b_cols * 256; p.b_chunk0 = b_chunk0; p.n_cols = n_cols; p.b_shift = b_shift;
     p.C = C; p.ldc = ldc; p.m_tiles = m_tiles; p.tiles = tiles; p.T = T; p.Tp = T + 2;
     int splits = num_sms() / m_tiles;
     if (splits < 1) splits = 1;

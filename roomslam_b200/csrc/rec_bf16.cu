@@ -1,0 +1,458 @@
+// Persistent tensor-core GRU recurrence for the bf16 mode (H = 128): forward and backward through time
+// (SURVEY.md 8(a) rows a3, a4).  One CTA owns 128 traces of ONE direction for all T steps.
+//
+// Forward, per step:   G[128 x 384] = h_{t-1}[128 x 128] . W_hh^T   on tcgen05 (bf16 operands, fp32 accumulator in TMEM)
+//   * W_hh (3H x H bf16, 96 KB) is loaded ONCE into shared memory and stays resident for the whole sequence;
+//   * h_{t-1} lives in shared memory as the A operand (no-swizzle core-matrix layout = the tile-major block layout);
+//   * 8 epilogue warps (256 threads; thread = trace row x 64 hidden units) pull the accumulator out of TMEM
+//     (tcgen05.ld), add the input-side pre-activation (layer 0: fused K=2 projection of the raw (x, y) sample;
+//     deeper layers: the time-parallel projection P), apply r/z/n with tanh.approx (sigma(a) = 0.5 tanh(a/2) + 0.5),
+//     blend h_t = n + z (h_{t-1} - n), and write h_t back into the A operand in place, to `out` and (training) the
+//     gates r, z, n, W_hn h + b_hn for the backward pass -- all with 16-byte accesses that are contiguous across
+//     the 32 rows of a warp (512 B per warp instruction) thanks to the tile-major layout;
+//   * one mbarrier hands h_t to the MMA-issuing warp, tcgen05.commit hands the accumulator back.
+// Backward, per step (reverse time):  dh_{t-1} = z (.) dh_t + dGh_t[128 x 384] . W_hh  on tcgen05, with W_hh^T resident
+//   in shared memory, dGh_t written by the epilogue warps as the A operand, the z (.) dh carry kept in fp32 registers.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "../../include/roomslam_b200.h"
+
+namespace {
+
+constexpr int H = 128;
+constexpr int CHUNK = 2048;                 // bytes of one 16-byte chunk column over 128 rows
+constexpr int W_BYTES = 3 * H * H * 2;      // 96 KB
+constexpr int A_FWD_BYTES = H * 128 * 2;    // 32 KB  (h tile)
+constexpr int A_BWD_BYTES = 3 * H * 128 * 2;  // 96 KB (dGh tile)
+constexpr int H32_BYTES = H * 128 * 4;      // 64 KB  (fp32 hidden state, forward)
+constexpr int NUM_THREADS = 320;            // warp 0: MMA issuer, warp 1: spare, warps 2..9: epilogue
+constexpr int EPI_THREADS = 256;
+
+struct FwdParams {
+    const float* x; int I;                  // layer 0: raw input (B, T, I <= 4), fused projection
+    const float4* wx;                       // [2][3H] packed (w0, w1, w2|0, bias) per gate row (bias = b_ih (+ b_hh for r, z))
+    const uint8_t* P; long long p_block_bytes;   // deeper layers: tile-major projection, C = 6H, bias folded in
+    const uint8_t* Whh;                     // [2][16][384][8] bf16 (B operand image)
+    const float* b_hn;                      // [2][H]
+    uint8_t* out; long long out_block_bytes;     // tile-major, C = 2H
+    uint8_t* gates;                         // [tiles][T][2][64][128][8] fp16 (private to fwd/bwd) or NULL
+    float* h_n;                             // [2][B][H]
+    int B, T;
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+    return __bfloat1622float2(h);
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    float2 a = bf2_to_f2(v.x), b = bf2_to_f2(v.y), c = bf2_to_f2(v.z), d = bf2_to_f2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    return make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]), f2_to_bf2(f[6], f[7]));
+}
+// saved gates are private to the two recurrence kernels: fp16 (r, z, n live in [-1, 1], where fp16 is 8x finer than bf16)
+__device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8h(const float* f) {
+    return make_uint4(f2_to_h2(f[0], f[1]), f2_to_h2(f[2], f[3]), f2_to_h2(f[4], f[5]), f2_to_h2(f[6], f[7]));
+}
+__device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;                               // [16 chunks][384 rows][16 B]
+    uint8_t* a_s = smem + W_BYTES;                     // [16 chunks][128 rows][16 B]  h_{t-1}
+    uint8_t* h32_s = a_s + A_FWD_BYTES;                // [32 chunks of 4 floats][128 rows][16 B]  fp32 master copy of h
+    float4* wx_s = reinterpret_cast<float4*>(h32_s + H32_BYTES);   // [3H] (layer 0)
+    float* bhn_s = reinterpret_cast<float*>(wx_s + 3 * H);        // [H]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bhn_s + H);
+    uint64_t* w_full = bars;
+    uint64_t* h_ready = bars + 1;       // epilogue -> MMA (8 arrivals, one per epilogue warp)
+    uint64_t* acc_full = bars + 2;      // MMA -> epilogue (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, dir = blockIdx.y;
+    const int T = p.T;
+
+    if (threadIdx.x == 0) {
+        rs::mbar_init(w_full, 1);
+        rs::mbar_init(h_ready, 8);
+        rs::mbar_init(acc_full, 1);
+        rs::fence_mbar_init();
+    }
+    if (warp == 0) rs::tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < 3 * H; i += NUM_THREADS)
+        wx_s[i] = p.x ? p.wx[dir * 3 * H + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < H; i += NUM_THREADS) bhn_s[i] = p.b_hn[dir * H + i];
+    for (int i = threadIdx.x; i < (A_FWD_BYTES + H32_BYTES) / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
+    rs::fence_proxy_async();            // the zeroed h_0 must be visible to the tensor core (async proxy)
+    rs::tc_fence_before();
+    __syncthreads();
+    rs::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== W loader + MMA issuer =====================
+        if (lane == 0) {
+            rs::mbar_expect_tx(w_full, W_BYTES);
+            for (int i = 0; i < 6; ++i)
+                rs::bulk_load(w_s + i * (W_BYTES / 6), p.Whh + (long long)dir * W_BYTES + i * (W_BYTES / 6), W_BYTES / 6, w_full);
+        }
+        rs::mbar_wait(w_full, 0);
+        constexpr uint32_t idesc256 = rs::umma_idesc_bf16(128, 256, 0, 0);
+        constexpr uint32_t idesc128 = rs::umma_idesc_bf16(128, 128, 0, 0);
+        const uint32_t a_addr = rs::smem_u32(a_s), w_addr = rs::smem_u32(w_s);
+        for (int step = 0; step < T; ++step) {
+            if (step > 0) {                       // h_0 = 0 is already in place for step 0
+                rs::mbar_wait(h_ready, (step - 1) & 1);
+                rs::tc_fence_after();
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t da = rs::umma_desc_noswz(a_addr + k * 2 * CHUNK, CHUNK, 128);
+                    const uint64_t db0 = rs::umma_desc_noswz(w_addr + k * 2 * (384 * 16), 384 * 16, 128);
+                    const uint64_t db1 = rs::umma_desc_noswz(w_addr + k * 2 * (384 * 16) + 256 * 16, 384 * 16, 128);
+                    rs::tc_mma_bf16(tmem_base, da, db0, idesc256, k != 0);          // r | z  -> columns [0, 256)
+                    rs::tc_mma_bf16(tmem_base + 256, da, db1, idesc128, k != 0);    // n      -> columns [256, 384)
+                }
+                rs::tc_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 2) {
+        // ===================== epilogue: gates, blend, stores =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;                        // TMEM lane quadrant of this warp
+        const int half = ew >> 2;                      // which 64 hidden units
+        const int row = q * 32 + lane;
+        const long long b = (long long)tile * 128 + row;
+        const bool live = b < p.B;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* a_row = a_s + row * 16;
+        uint8_t* h32_row = h32_s + row * 16;
+        const float* xrow = p.x ? p.x + b * T * p.I : nullptr;
+
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? (T - 1 - step) : step;
+            const long long blk = (long long)tile * (T + 2) + t + 1;
+            const uint8_t* pblk = p.P ? p.P + blk * p.p_block_bytes + (long long)(dir * 48) * CHUNK + row * 16 : nullptr;
+            uint8_t* oblk = p.out + blk * p.out_block_bytes + (long long)(dir * 16) * CHUNK + row * 16;
+            uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK) + row * 16 : nullptr;
+            float xin[4] = {0.f, 0.f, 0.f, 0.f};
+            if (xrow && live) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < p.I) xin[c] = __ldg(xrow + (long long)t * p.I + c);
+            }
+            // input-side pre-activations of the first sub-chunk are fetched before waiting for the tensor core
+            uint4 pv[6];
+            if (pblk) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    pv[2 * g] = ldg16(pblk + (long long)(g * 16 + half * 8) * CHUNK);
+                    pv[2 * g + 1] = ldg16(pblk + (long long)(g * 16 + half * 8 + 1) * CHUNK);
+                }
+            }
+            rs::mbar_wait(acc_full, step & 1);
+            rs::tc_fence_after();
+#pragma unroll 1
+            for (int sc = 0; sc < 4; ++sc) {
+                const int u0 = half * 64 + sc * 16;
+                uint32_t ar[16], az[16], an[16];
+                rs::tmem_ld_32x32b_x16(taddr + u0, ar);
+                rs::tmem_ld_32x32b_x16(taddr + 128 + u0, az);
+                rs::tmem_ld_32x32b_x16(taddr + 256 + u0, an);
+                float pr[16], pz[16], pn[16], ho[16];
+                if (pblk) {
+                    unpack8(pv[0], pr); unpack8(pv[1], pr + 8);
+                    unpack8(pv[2], pz); unpack8(pv[3], pz + 8);
+                    unpack8(pv[4], pn); unpack8(pv[5], pn + 8);
+                    if (sc < 3) {       // prefetch the next sub-chunk
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) {
+                            pv[2 * g] = ldg16(pblk + (long long)(g * 16 + half * 8 + 2 * (sc + 1)) * CHUNK);
+                            pv[2 * g + 1] = ldg16(pblk + (long long)(g * 16 + half * 8 + 2 * (sc + 1) + 1) * CHUNK);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 wr = wx_s[u0 + j], wz = wx_s[H + u0 + j], wn = wx_s[2 * H + u0 + j];
+                        pr[j] = fmaf(wr.z, xin[2], fmaf(wr.y, xin[1], fmaf(wr.x, xin[0], wr.w)));
+                        pz[j] = fmaf(wz.z, xin[2], fmaf(wz.y, xin[1], fmaf(wz.x, xin[0], wz.w)));
+                        pn[j] = fmaf(wn.z, xin[2], fmaf(wn.y, xin[1], fmaf(wn.x, xin[0], wn.w)));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {       // fp32 h_{t-1}: the blend must not re-round the state every step
+                    const float4 v = *reinterpret_cast<const float4*>(h32_row + (u0 / 4 + j) * CHUNK);
+                    ho[4 * j] = v.x; ho[4 * j + 1] = v.y; ho[4 * j + 2] = v.z; ho[4 * j + 3] = v.w;
+                }
+                rs::tmem_ld_wait();
+                float hv[16], rv[16], zv[16], nv[16], hnv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float r = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(ar[j]) + pr[j])), 0.5f);
+                    const float z = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(az[j]) + pz[j])), 0.5f);
+                    const float hn = __uint_as_float(an[j]) + bhn_s[u0 + j];
+                    const float n = tanh_fast(fmaf(r, hn, pn[j]));
+                    hv[j] = fmaf(z, ho[j] - n, n);
+                    rv[j] = r; zv[j] = z; nv[j] = n; hnv[j] = hn;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(h32_row + (u0 / 4 + j) * CHUNK) = make_float4(hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
+                const uint4 o0 = pack8(hv), o1 = pack8(hv + 8);
+                *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK) = o0;      // next step's A operand, in place
+                *reinterpret_cast<uint4*>(a_row + (u0 / 8 + 1) * CHUNK) = o1;
+                stg16(oblk + (long long)(u0 / 8) * CHUNK, o0);
+                stg16(oblk + (long long)(u0 / 8 + 1) * CHUNK, o1);
+                if (gblk) {
+                    stg16(gblk + (long long)(0 * 16 + u0 / 8) * CHUNK, pack8h(rv));
+                    stg16(gblk + (long long)(0 * 16 + u0 / 8 + 1) * CHUNK, pack8h(rv + 8));
+                    stg16(gblk + (long long)(1 * 16 + u0 / 8) * CHUNK, pack8h(zv));
+                    stg16(gblk + (long long)(1 * 16 + u0 / 8 + 1) * CHUNK, pack8h(zv + 8));
+                    stg16(gblk + (long long)(2 * 16 + u0 / 8) * CHUNK, pack8h(nv));
+                    stg16(gblk + (long long)(2 * 16 + u0 / 8 + 1) * CHUNK, pack8h(nv + 8));
+                    stg16(gblk + (long long)(3 * 16 + u0 / 8) * CHUNK, pack8h(hnv));
+                    stg16(gblk + (long long)(3 * 16 + u0 / 8 + 1) * CHUNK, pack8h(hnv + 8));
+                }
+                if (step == T - 1 && live) {
+                    float* hn_out = p.h_n + ((long long)dir * p.B + b) * H + u0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(hn_out + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
+                }
+            }
+            rs::fence_proxy_async();        // h_t written with ordinary stores -> visible to tcgen05.mma
+            rs::tc_fence_before();          // our TMEM reads are done before the next MMA overwrites the accumulator
+            __syncwarp();
+            if (lane == 0) rs::mbar_arrive(h_ready);
+        }
+    }
+    rs::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) rs::tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct BwdParams {
+    const uint8_t* d_out; long long dout_block_bytes;    // tile-major C = 2H gradient w.r.t. this layer's output, or NULL
+    const float* d_h_n;                                  // [2][B][H] or NULL
+    const uint8_t* gates;                                // [tiles][T][2][64][128][8]
+    const uint8_t* out; long long out_block_bytes;       // this layer's h (tile-major, C = 2H, zero pad rows)
+    const uint8_t* WhhT;                                 // [2][48][128][8] bf16: rows = h index, K = (r | z | hn) gate rows
+    uint8_t* dG; long long dg_block_bytes;               // tile-major C = 8H: [dir][r | z | n | hn][H]
+    int B, T;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;                               // [48 chunks][128 rows][16 B]
+    uint8_t* a_s = smem + W_BYTES;                     // [48 chunks][128 rows][16 B]  dGh_t
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + A_BWD_BYTES);
+    uint64_t* w_full = bars;
+    uint64_t* a_ready = bars + 1;
+    uint64_t* acc_full = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, dir = blockIdx.y;
+    const int T = p.T;
+
+    if (threadIdx.x == 0) {
+        rs::mbar_init(w_full, 1);
+        rs::mbar_init(a_ready, 8);
+        rs::mbar_init(acc_full, 1);
+        rs::fence_mbar_init();
+    }
+    if (warp == 0) rs::tmem_alloc<128>(tmem_slot);
+    rs::tc_fence_before();
+    __syncthreads();
+    rs::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            rs::mbar_expect_tx(w_full, W_BYTES);
+            for (int i = 0; i < 6; ++i)
+                rs::bulk_load(w_s + i * (W_BYTES / 6), p.WhhT + (long long)dir * W_BYTES + i * (W_BYTES / 6), W_BYTES / 6, w_full);
+        }
+        rs::mbar_wait(w_full, 0);
+        constexpr uint32_t idesc = rs::umma_idesc_bf16(128, 128, 0, 0);
+        const uint32_t a_addr = rs::smem_u32(a_s), w_addr = rs::smem_u32(w_s);
+        for (int s = 0; s < T - 1; ++s) {              // the result of the last reverse step (dh before t = first) is unused
+            rs::mbar_wait(a_ready, s & 1);
+            rs::tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 24; ++k) {
+                    const uint64_t da = rs::umma_desc_noswz(a_addr + k * 2 * CHUNK, CHUNK, 128);
+                    const uint64_t db = rs::umma_desc_noswz(w_addr + k * 2 * CHUNK, CHUNK, 128);
+                    rs::tc_mma_bf16(tmem_base, da, db, idesc, k != 0);
+                }
+                rs::tc_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 2) {
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int row = q * 32 + lane;
+        const long long b = (long long)tile * 128 + row;
+        const bool live = b < p.B;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* a_row = a_s + row * 16;
+        float carry[64];                                // z (.) dh of the step processed before (fp32, registers)
+#pragma unroll
+        for (int j = 0; j < 64; ++j) carry[j] = 0.0f;
+        if (p.d_h_n && live) {
+            const float* src = p.d_h_n + ((long long)dir * p.B + b) * H + half * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + j));
+                carry[j] = v.x; carry[j + 1] = v.y; carry[j + 2] = v.z; carry[j + 3] = v.w;
+            }
+        }
+        for (int s = 0; s < T; ++s) {                   // s-th reverse step = forward position T-1-s
+            const int fstep = T - 1 - s;
+            const int t = dir ? (T - 1 - fstep) : fstep;
+            const int t_prev = dir ? t + 1 : t - 1;     // time row of h_{prev}; the pad rows hold the zero initial state
+            const long long blk = (long long)tile * (T + 2) + t + 1;
+            const long long blk_prev = (long long)tile * (T + 2) + t_prev + 1;
+            const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK) + row * 16;
+            const uint8_t* hblk = p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16) * CHUNK + row * 16;
+            const uint8_t* doblk = p.d_out ? p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16) * CHUNK + row * 16 : nullptr;
+            uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 64) * CHUNK + row * 16;
+            if (s > 0) {
+                rs::mbar_wait(acc_full, (s - 1) & 1);
+                rs::tc_fence_after();
+            }
+#pragma unroll
+            for (int sc = 0; sc < 4; ++sc) {
+                const int c0 = half * 8 + sc * 2;       // first of the two 8-unit chunks of this sub-chunk
+                uint32_t acc[16];
+                if (s > 0) rs::tmem_ld_32x32b_x16(taddr + half * 64 + sc * 16, acc);
+                float r[16], z[16], n[16], hn[16], hp[16], dout[16];
+                unpack8h(ldg16(gblk + (long long)(0 * 16 + c0) * CHUNK), r);  unpack8h(ldg16(gblk + (long long)(0 * 16 + c0 + 1) * CHUNK), r + 8);
+                unpack8h(ldg16(gblk + (long long)(1 * 16 + c0) * CHUNK), z);  unpack8h(ldg16(gblk + (long long)(1 * 16 + c0 + 1) * CHUNK), z + 8);
+                unpack8h(ldg16(gblk + (long long)(2 * 16 + c0) * CHUNK), n);  unpack8h(ldg16(gblk + (long long)(2 * 16 + c0 + 1) * CHUNK), n + 8);
+                unpack8h(ldg16(gblk + (long long)(3 * 16 + c0) * CHUNK), hn); unpack8h(ldg16(gblk + (long long)(3 * 16 + c0 + 1) * CHUNK), hn + 8);
+                unpack8(ldg16(hblk + (long long)c0 * CHUNK), hp);            unpack8(ldg16(hblk + (long long)(c0 + 1) * CHUNK), hp + 8);
+                if (doblk) {
+                    unpack8(ldg16(doblk + (long long)c0 * CHUNK), dout);     unpack8(ldg16(doblk + (long long)(c0 + 1) * CHUNK), dout + 8);
+                }
+                if (s > 0) rs::tmem_ld_wait();
+                float gr[16], gz[16], gn[16], ghn[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float dh = carry[sc * 16 + j];
+                    if (s > 0) dh += __uint_as_float(acc[j]);
+                    if (doblk) dh += dout[j];
+                    const float dn = dh * (1.0f - z[j]);
+                    const float dz = dh * (hp[j] - n[j]);
+                    gn[j] = dn * (1.0f - n[j] * n[j]);
+                    gz[j] = dz * z[j] * (1.0f - z[j]);
+                    ghn[j] = gn[j] * r[j];
+                    gr[j] = gn[j] * hn[j] * r[j] * (1.0f - r[j]);
+                    carry[sc * 16 + j] = dh * z[j];
+                }
+                const uint4 vr0 = pack8(gr), vr1 = pack8(gr + 8), vz0 = pack8(gz), vz1 = pack8(gz + 8);
+                const uint4 vn0 = pack8(gn), vn1 = pack8(gn + 8), vh0 = pack8(ghn), vh1 = pack8(ghn + 8);
+                // A operand of the dh matvec: K order r | z | hn
+                *reinterpret_cast<uint4*>(a_row + (0 * 16 + c0) * CHUNK) = vr0;
+                *reinterpret_cast<uint4*>(a_row + (0 * 16 + c0 + 1) * CHUNK) = vr1;
+                *reinterpret_cast<uint4*>(a_row + (1 * 16 + c0) * CHUNK) = vz0;
+                *reinterpret_cast<uint4*>(a_row + (1 * 16 + c0 + 1) * CHUNK) = vz1;
+                *reinterpret_cast<uint4*>(a_row + (2 * 16 + c0) * CHUNK) = vh0;
+                *reinterpret_cast<uint4*>(a_row + (2 * 16 + c0 + 1) * CHUNK) = vh1;
+                stg16(dgblk + (long long)(0 * 16 + c0) * CHUNK, vr0); stg16(dgblk + (long long)(0 * 16 + c0 + 1) * CHUNK, vr1);
+                stg16(dgblk + (long long)(1 * 16 + c0) * CHUNK, vz0); stg16(dgblk + (long long)(1 * 16 + c0 + 1) * CHUNK, vz1);
+                stg16(dgblk + (long long)(2 * 16 + c0) * CHUNK, vn0); stg16(dgblk + (long long)(2 * 16 + c0 + 1) * CHUNK, vn1);
+                stg16(dgblk + (long long)(3 * 16 + c0) * CHUNK, vh0); stg16(dgblk + (long long)(3 * 16 + c0 + 1) * CHUNK, vh1);
+            }
+            rs::fence_proxy_async();
+            rs::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) rs::mbar_arrive(a_ready);
+        }
+    }
+    rs::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) rs::tmem_dealloc<128>(tmem_base);
+}
+
+}  // namespace
+
+extern "C" int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, const void* P, int64_t p_cols, const void* Whh,
+                               const float* b_hn, void* out, void* gates, float* h_n, int B, int T, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE((x != nullptr) != (P != nullptr), "rs_rec_fwd_bf16: exactly one of x (layer 0) and P (deeper layers) must be given");
+    RS_REQUIRE(!x || (I >= 1 && I <= 3 && wx_packed), "rs_rec_fwd_bf16: fused input projection needs 1 <= I <= 3 and packed weights");
+    RS_REQUIRE(!P || p_cols == 6 * H, "rs_rec_fwd_bf16: P must have 6H = %d columns", 6 * H);
+    RS_REQUIRE(Whh && b_hn && out && h_n && B >= 0 && T >= 0, "rs_rec_fwd_bf16: bad arguments");
+    if (B == 0) return 0;
+    if (T == 0) {
+        RS_CUDA_OK(cudaMemsetAsync(h_n, 0, sizeof(float) * 2 * (size_t)B * H, stream));
+        return 0;
+    }
+    FwdParams p = {};
+    p.x = x; p.I = I; p.wx = reinterpret_cast<const float4*>(wx_packed);
+    p.P = static_cast<const uint8_t*>(P); p.p_block_bytes = 6LL * H * 256;
+    p.Whh = static_cast<const uint8_t*>(Whh); p.b_hn = b_hn;
+    p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
+    p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.B = B; p.T = T;
+    const int smem = W_BYTES + A_FWD_BYTES + H32_BYTES + 3 * H * 16 + H * 4 + 64;
+    RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rec_fwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT,
+                               void* dG, int B, int T, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(gates && out && WhhT && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
+    if (B == 0 || T == 0) return 0;
+    BwdParams p = {};
+    p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
+    p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);
+    p.out = static_cast<const uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
+    p.WhhT = static_cast<const uint8_t*>(WhhT);
+    p.dG = static_cast<uint8_t*>(dG); p.dg_block_bytes = 8LL * H * 256;
+    p.B = B; p.T = T;
+    const int smem = W_BYTES + A_BWD_BYTES + 64;
+    RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rec_bwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -119,16 +119,18 @@ def padded(B: int, T: int, C: int, device, dtype=torch.float32) -> torch.Tensor:
 class GRULayerFn(torch.autograd.Function):
     """ONE bidirectional GRU layer, fp32 kernels.
 
-    apply(xin, padded_in, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+    apply(xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         -> (out_padded (B, T+2, 2H), h_n (2, B, H))
+    meta = (padded_in, B, T).
     xin : padded_in False: the traces (B, T, I);  True: the padded output (B, T+2, I) of the layer below.
     mask: None or (B, T, I) dropout keep-mask (scaled by 1/(1-p)) applied to xin (decision D4).
     One Function per layer, so a layer's weight gradients are final (and can be all-reduced) while the
     backward-through-time of the layer below is still running."""
 
     @staticmethod
-    def forward(ctx, xin, padded_in, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+    def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         _need_cuda(xin, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        padded_in = meta[0]
         xin = xin.contiguous().float()
         ctx.padded_in_orig = bool(padded_in)
         B, Il = xin.shape[0], xin.shape[2]
@@ -225,14 +227,29 @@ class GRULayerFn(torch.autograd.Function):
 def gru_encoder(x, mask, num_layers, weights, layer_fn=None):
     """Stack of bidirectional layers -> (out (B,T,2H) of the top layer, h_n (2L,B,H)), torch.nn.GRU semantics."""
     layer_fn = layer_fn or GRULayerFn
-    T = x.shape[1]
+    B, T = x.shape[0], x.shape[1]
     cur, padded_in, h_all = x, False, []
     for l in range(num_layers):
         m = mask[l - 1] if (mask is not None and l > 0) else None
-        cur, h_n = layer_fn.apply(cur, padded_in, m, *weights[8 * l: 8 * l + 8])
+        cur, h_n = layer_fn.apply(cur, (padded_in, B, T), m, *weights[8 * l: 8 * l + 8])
         padded_in = True
         h_all.append(h_n)
-    return cur[:, 1:T + 1, :], (torch.cat(h_all, 0) if num_layers > 1 else h_all[0])
+    h_n = torch.cat(h_all, 0) if num_layers > 1 else h_all[0]
+    if cur.dim() == 5:                       # bf16 mode: tile-major -> (B, T, 2H); only materialised when it is used
+        from . import layout
+        return _LazyOut(cur, B, T), h_n
+    return cur[:, 1:T + 1, :], h_n
+
+
+class _LazyOut:
+    """Top-layer output of the bf16 mode, kept tile-major until somebody asks for the (B, T, 2H) tensor."""
+
+    def __init__(self, tm, B, T):
+        self.tm, self.B, self.T = tm, B, T
+
+    def materialize(self) -> torch.Tensor:
+        from . import layout
+        return layout.from_tile_major(self.tm, self.B, self.T).float()
 
 
 class DecoderFn(torch.autograd.Function):

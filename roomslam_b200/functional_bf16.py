@@ -1,0 +1,172 @@
+"""bf16 tensor-core mode of the GRU encoder: orchestration of the tcgen05 kernels (hidden_size = 128).
+
+Per layer:   layer 0: fused K=2 input projection inside the recurrence kernel
+             deeper : P = X W_ih^T + b           rs_blk_gemm_nt   (tcgen05, bulk-copy fed)
+             recurrence forward                  rs_rec_fwd_bf16  (persistent, W_hh resident in shared memory)
+backward:    recurrence backward (BPTT)          rs_rec_bwd_bf16  -> dG (r | z | n | hn gate gradients)
+             dW_hh  = dG[r,z,hn]^T h_{t-/+1}     rs_blk_gemm_tn_acc (time-shifted block pairing)
+             dW_ih  = dG[r,z,n]^T X, bias grads  rs_blk_gemm_tn_acc (ones column)
+             dX     = dG[r,z,n] W_ih             rs_blk_gemm_nt
+All per-timestep activations stay in the tile-major bf16 layout (roomslam_b200/layout.py); master weights and
+weight gradients are fp32.  Tolerance against the fp32 CPU oracle: 2e-2 relative (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from . import layout as L
+from .functional import _need_cuda, _p, _stream, ktime
+
+H = 128
+
+
+def _nt(A, a_cols, kchunks, W_tiled, n_tiles, C, c_cols, c_chunk0, bias, n_blocks, st):
+    kch = L.int_array(kchunks)
+    _lib.call("rs_blk_gemm_nt", _p(A), a_cols, ctypes.addressof(kch), len(kchunks), _p(W_tiled), n_tiles, _p(C), c_cols,
+              c_chunk0, _p(bias), n_blocks, st)
+
+
+def _tn(A, a_cols, mchunks, rows, Bm, b_cols, b_chunk0, n_cols, shift, bcast, C, ldc, tiles, T, st):
+    mch, r0 = L.int_array(mchunks), L.int_array(rows)
+    _lib.call("rs_blk_gemm_tn_acc", _p(A), a_cols, ctypes.addressof(mch), ctypes.addressof(r0), len(mchunks), _p(Bm), b_cols,
+              b_chunk0, n_cols, shift, int(bcast), _p(C), ldc, tiles, T, st)
+
+
+_ONES = {}
+
+
+def _ones_block(device):
+    """One tile-major block with 16 columns whose first column is 1: B operand that turns a TN GEMM into column sums."""
+    key = str(device)
+    if key not in _ONES:
+        blk = torch.zeros(2, L.TILE, 8, device=device, dtype=torch.bfloat16)
+        blk[0, :, 0] = 1.0
+        _ONES[key] = blk
+    return _ONES[key]
+
+
+class GRULayerBF16Fn(torch.autograd.Function):
+    """apply(xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r) -> (out tile-major bf16, h_n (2,B,H) fp32)
+    meta = (padded_in, B, T).  padded_in False: xin is the raw trace batch (B, T, I) fp32 (layer 0);
+    True: xin is the tile-major bf16 output of the layer below."""
+
+    @staticmethod
+    def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        _need_cuda(xin, mask, w_ih, w_hh)
+        padded_in, B, T = meta
+        if w_hh.shape[1] != H:
+            raise _lib.RoomSlamError(f"bf16 mode is built for hidden_size = {H} (got {w_hh.shape[1]}); use precision='fp32'")
+        dev = xin.device
+        st = _stream(xin)
+        need_grad = any(ctx.needs_input_grad)
+        tiles = L.n_tiles(B)
+        Il = w_ih.shape[1]
+        with torch.no_grad():
+            w_ih_cat = torch.cat([w_ih, w_ih_r], 0).float()                       # [6H, Il]
+            w_hh_cat = torch.stack([w_hh, w_hh_r], 0).float()                     # [2, 3H, H]
+            whh_img = w_hh_cat.to(torch.bfloat16).view(2, 3 * H, H // 8, 8).permute(0, 2, 1, 3).contiguous()
+            b_hn = torch.stack([b_hh[2 * H:], b_hh_r[2 * H:]], 0).float().contiguous()
+            bias_x = torch.stack([b_ih, b_ih_r], 0).float().clone()               # [2, 3H]
+            bias_x[0, :2 * H] += b_hh[:2 * H]
+            bias_x[1, :2 * H] += b_hh_r[:2 * H]
+            out = L.empty_tm(B, T, 2 * H, dev)
+            h_n = torch.empty(2, B, H, device=dev)
+            gates = torch.empty(tiles, T, 2, 64, L.TILE, 8, device=dev, dtype=torch.bfloat16) if need_grad else None
+            rec_flops = 2.0 * B * T * 2 * 3 * H * H
+            X = None
+            if not padded_in:
+                if Il > 3:
+                    raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 3")
+                x = xin.contiguous().float()
+                wx = torch.zeros(2, 3 * H, 4, device=dev)
+                wx[:, :, :Il] = w_ih_cat.view(2, 3 * H, Il)
+                wx[:, :, 3] = bias_x
+                with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
+                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, _p(wx), 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n),
+                              B, T, st)
+                saved_in = x
+            else:
+                X = xin
+                if mask is not None:
+                    X = (xin * L.to_tile_major(mask)).contiguous()
+                P = torch.empty(tiles, T + 2, 6 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
+                wt = L.tile_weight_nt(w_ih_cat)                                    # [6][Il/64][8][128][8]
+                with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
+                    _nt(X, Il, [8 * k for k in range(Il // 64)], wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
+                        tiles * (T + 2), st)
+                with ktime("rec_fwd_bf16_kernel", rec_flops):
+                    _lib.call("rs_rec_fwd_bf16", 0, 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n),
+                              B, T, st)
+                del P
+                saved_in = X
+        ctx.meta = (padded_in, B, T, Il)
+        ctx.mask = mask
+        ctx.saved = (out, gates, saved_in, w_ih_cat, w_hh_cat)
+        return out, h_n
+
+    @staticmethod
+    def backward(ctx, d_out, d_h_n):
+        padded_in, B, T, Il = ctx.meta
+        out, gates, saved_in, w_ih_cat, w_hh_cat = ctx.saved
+        if gates is None:
+            raise RuntimeError("GRULayerBF16Fn: forward ran without saving activations (nothing required grad)")
+        dev = out.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        tiles = L.n_tiles(B)
+        with torch.no_grad():
+            d_out = d_out.contiguous().to(torch.bfloat16) if d_out is not None else None
+            d_h_n = d_h_n.contiguous().float() if d_h_n is not None else None
+            whhT_img = w_hh_cat.transpose(1, 2).to(torch.bfloat16).contiguous().view(2, H, 3 * H // 8, 8) \
+                .permute(0, 2, 1, 3).contiguous()                                  # [2][48][128][8]
+            dG = torch.empty(tiles, T + 2, 8 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
+            dG[:, 0].zero_()
+            dG[:, T + 1].zero_()
+            with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
+                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), B, T, st)
+            # hidden-side weight gradients: dG(t') pairs with h(t'-1) (forward) / h(t'+1) (reverse)
+            dW_hh = torch.zeros(2, 3 * H, H, device=dev)
+            with ktime("blk_gemm_tn_kernel(wgrad)", 2.0 * tiles * L.TILE * T * 6 * H * H):
+                for d in (0, 1):
+                    _tn(dG, 8 * H, [d * 64 + 0, d * 64 + 16, d * 64 + 48], [0, H, 2 * H], out, 2 * H, d * 16, H,
+                        -1 if d == 0 else 1, False, dW_hh[d], H, tiles, T, st)
+            # bias gradients: column sums of the eight gate blocks (ones column as the B operand)
+            sums = torch.zeros(8 * H, 16, device=dev)
+            with ktime("blk_gemm_tn_kernel(bias)", 2.0 * tiles * L.TILE * T * 8 * H * 16):
+                _tn(dG, 8 * H, [16 * i for i in range(8)], [H * i for i in range(8)], _ones_block(dev), 16, 0, 16, 0, True,
+                    sums, 16, tiles, T, st)
+            s = sums[:, 0].view(2, 4, H)
+            db_ih = s[:, :3].reshape(2, 3 * H)
+            db_hh = torch.cat([s[:, :2].reshape(2, 2 * H), s[:, 3]], 1)
+            # input-side weight gradients
+            d_xin = None
+            if not padded_in:
+                x = saved_in
+                xa = torch.zeros(B, T, 16, device=dev)
+                xa[:, :, :Il] = x
+                xa_tm = L.to_tile_major(xa)
+                dW = torch.zeros(6 * H, 16, device=dev)
+                with ktime("blk_gemm_tn_kernel(wgrad)", 2.0 * tiles * L.TILE * T * 6 * H * 16):
+                    _tn(dG, 8 * H, [d * 64 + g * 16 for d in (0, 1) for g in (0, 1, 2)], [H * i for i in range(6)], xa_tm, 16, 0,
+                        16, 0, False, dW, 16, tiles, T, st)
+                dW_ih = dW[:, :Il].contiguous()
+            else:
+                X = saved_in
+                dW_ih = torch.zeros(6 * H, Il, device=dev)
+                with ktime("blk_gemm_tn_kernel(wgrad)", 2.0 * tiles * L.TILE * T * 6 * H * Il):
+                    for c0 in range(0, Il, 256):
+                        _tn(dG, 8 * H, [d * 64 + g * 16 for d in (0, 1) for g in (0, 1, 2)], [H * i for i in range(6)], X, Il,
+                            c0 // 8, min(256, Il - c0), 0, False, dW_ih[:, c0:], Il, tiles, T, st)
+                if ctx.needs_input_grad[0]:
+                    dX = torch.empty(tiles, T + 2, Il // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
+                    wt = L.tile_weight_nt(w_ih_cat.t().contiguous())               # [Il/128][12][8][128][8]
+                    kch = [d * 64 + g * 16 + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in (0, 1)]
+                    with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
+                        _nt(dG, 8 * H, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
+                    if ctx.mask is not None:
+                        dX = (dX * L.to_tile_major(ctx.mask)).contiguous()
+                    d_xin = dX
+        return (d_xin, None, None, dW_ih[:3 * H], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * H:], dW_hh[1], db_ih[1], db_hh[1])

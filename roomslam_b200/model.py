@@ -112,11 +112,24 @@ class RoomSLAM(nn.Module):
             if dropout_mask.dim() == 3:
                 dropout_mask = dropout_mask.unsqueeze(0)
             dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
+        out, h_n = self._encode(x, dropout_mask)
+        if isinstance(out, F_._LazyOut):
+            out = out.materialize()
+        return out, h_n
+
+    def _encode(self, x, dropout_mask):
         layer_fn = F_.GRULayerFn if self.precision == "fp32" else _bf16_layer_fn()
         return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn)
 
     def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        _, h_n = self.encode(x, dropout_mask)
+        self._check_input(x)
+        if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
+            dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
+        if dropout_mask is not None:
+            if dropout_mask.dim() == 3:
+                dropout_mask = dropout_mask.unsqueeze(0)
+            dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
+        _, h_n = self._encode(x, dropout_mask)
         latent = torch.cat([h_n[-2], h_n[-1]], dim=-1)          # decision D5 (README.md:115)
         return self.decoder(latent)
 

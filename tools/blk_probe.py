@@ -34,7 +34,7 @@ def tn(B, T, Ca, mcols, Cb, b_col0, n_cols, shift):
     C = torch.ones(M, n_cols, device=dev)
     mch = L.int_array([c // 8 for c in mcols]); rows = L.int_array([i * 128 for i in range(len(mcols))])
     _lib.call("rs_blk_gemm_tn_acc", at.data_ptr(), Ca, ctypes.addressof(mch), ctypes.addressof(rows), len(mcols), bt.data_ptr(), Cb,
-              b_col0 // 8, n_cols, shift, C.data_ptr(), n_cols, at.shape[0], T, st())
+              b_col0 // 8, n_cols, shift, 0, C.data_ptr(), n_cols, at.shape[0], T, st())
     torch.cuda.synchronize()
     aa = torch.cat([a[..., c:c + 128] for c in mcols], -1).bfloat16().float()          # (B,T,M)
     bb = torch.zeros(B, T, n_cols, device=dev)
