@@ -125,6 +125,12 @@ int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blo
 int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles, const void* B,
                        int64_t b_cols, int b_chunk0, int n_cols, int b_shift, int b_broadcast, float* C, int64_t ldc,
                        int tiles, int T, void* stream);
+/* Fused weight-gradient pass of one layer: every role r < n_roles accumulates C[r][128, n_cols[r]] += sum over blocks
+ * dG_blk[:, a_mchunk[r]*8 .. +128]^T . B[r]_blk'[:, b_chunk0[r]*8 .. + n_cols[r]] (time shift b_shift[r]) and, when
+ * bias[r] != NULL, bias[r][128] += column sums of the same dG columns.  All arrays are HOST arrays of length n_roles. */
+int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_roles, const int* a_mchunk,
+                 const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols, const int* b_shift,
+                 float* const* C, const int64_t* ldc, float* const* bias, int tiles, int T, void* stream);
 /* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
 /* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 3) fp32 + wx_packed [2][3H][4] = (w_ih row, bias);
  * deeper layers: P tile-major (6H columns, bias folded in).  Whh [2][16][384][8] bf16, b_hn [2][H], out tile-major

@@ -263,6 +263,136 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_tn_kernel(const TnPar
     if (warp == 1) rs::tmem_dealloc<256>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused weight-gradient pass: ONE launch computes every dW_ih / dW_hh / bias-gradient block of a layer.
+// A "role" = one 128-column block of dG (one gate of one direction) against one B source:
+//     C_role[128, n_cols] += sum over blocks  dG_blk[:, role columns]^T . B_blk'[:, ...]      (B_blk' time-shifted by b_shift)
+//     bias_role[128]      += sum over blocks  dG_blk[:, role columns]^T . 1                    (extra N=16 MMA on a ones tile)
+// Work item = (split of the block range, role); the roles of one split sit on neighbouring CTAs and walk the same
+// blocks at the same time, so a dG piece needed by two roles (and the B blocks shared by several) come from HBM once
+// and from L2 afterwards: dG is streamed from DRAM exactly once per layer instead of once per consumer.
+constexpr int WG_MAX_ROLES = 12;
+struct WgRole {
+    int a_mchunk;                       // first 16-byte chunk of the dG columns of this role
+    const uint8_t* B; long long b_block_bytes; int b_chunk0; int n_cols; int b_shift;
+    float* C; long long ldc;            // C rows [0,128) x n_cols of this role
+    float* bias;                        // 128 floats or NULL
+};
+struct WgParams {
+    const uint8_t* A; long long a_block_bytes;
+    const uint8_t* ones;                // [2 chunks][128][8] bf16, first column = 1
+    WgRole role[WG_MAX_ROLES];
+    int n_roles, tiles, T, Tp, splits, blocks_per_split, max_b_bytes;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int stage_bytes = 2 * PIECE_BYTES + p.max_b_bytes;
+    uint8_t* stages = smem;
+    uint8_t* ones_s = smem + 2 * stage_bytes;                    // 4 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + 2 * CHUNK_BYTES);
+    uint64_t* full_bar = bars;        // [2]
+    uint64_t* empty_bar = bars + 2;   // [2]
+    uint64_t* acc_full = bars + 4;
+    uint64_t* ones_full = bars + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 2; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], 1); }
+        rs::mbar_init(acc_full, 1);
+        rs::mbar_init(ones_full, 1);
+        rs::fence_mbar_init();
+    }
+    if (warp == 1) rs::tmem_alloc<512>(tmem_slot);
+    rs::tc_fence_before();
+    __syncthreads();
+    rs::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_blocks = p.tiles * p.T;
+    const int items = p.n_roles * p.splits;
+    int stage = 0; uint32_t phase = 0, acc_phase = 0;
+    if (warp == 0 && lane == 0) {
+        rs::mbar_expect_tx(ones_full, 2 * CHUNK_BYTES);
+        rs::bulk_load(ones_s, p.ones, 2 * CHUNK_BYTES, ones_full);
+    }
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const WgRole& R = p.role[item % p.n_roles];
+        const int split = item / p.n_roles;
+        const int i0 = split * p.blocks_per_split;
+        const int i1 = min(total_blocks, i0 + p.blocks_per_split);
+        const int b_bytes = R.n_cols * 256;
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int i = i0; i < i1; ++i) {
+                    const long long blk = (long long)(i / p.T) * p.Tp + 1 + (i % p.T);
+                    rs::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = stages + stage * stage_bytes;
+                    rs::mbar_expect_tx(&full_bar[stage], 2 * PIECE_BYTES + b_bytes);
+                    rs::bulk_load(sa, p.A + blk * p.a_block_bytes + (long long)R.a_mchunk * CHUNK_BYTES, 2 * PIECE_BYTES, &full_bar[stage]);
+                    rs::bulk_load(sa + 2 * PIECE_BYTES, R.B + (blk + R.b_shift) * R.b_block_bytes + (long long)R.b_chunk0 * CHUNK_BYTES,
+                                  b_bytes, &full_bar[stage]);
+                    if (++stage == 2) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t idesc = rs::umma_idesc_bf16(128, R.n_cols, 1, 1);
+            const uint32_t idesc1 = rs::umma_idesc_bf16(128, 16, 1, 1);
+            rs::mbar_wait(ones_full, 0);
+            const uint32_t so = rs::smem_u32(ones_s);
+            for (int i = i0; i < i1; ++i) {
+                rs::mbar_wait(&full_bar[stage], phase);
+                rs::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = rs::smem_u32(stages + stage * stage_bytes);
+                    const uint32_t sb = sa + 2 * PIECE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {       // 128 traces = 8 K-steps of 16
+                        const uint64_t da = rs::umma_desc_noswz(sa + k * 256, 128, CHUNK_BYTES);
+                        const uint64_t db = rs::umma_desc_noswz(sb + k * 256, 128, CHUNK_BYTES);
+                        rs::tc_mma_bf16(tmem_base, da, db, idesc, (i != i0) || (k != 0));
+                        if (R.bias) {
+                            const uint64_t d1 = rs::umma_desc_noswz(so + k * 256, 128, CHUNK_BYTES);
+                            rs::tc_mma_bf16(tmem_base + 256, da, d1, idesc1, (i != i0) || (k != 0));
+                        }
+                    }
+                    rs::tc_commit(&empty_bar[stage]);
+                    if (i == i1 - 1) rs::tc_commit(acc_full);
+                }
+                __syncwarp();
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        } else if (i1 > i0) {
+            const int q = warp & 3, row = q * 32 + lane;
+            rs::mbar_wait(acc_full, acc_phase);
+            rs::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+            float* crow = R.C + (long long)row * R.ldc;
+            for (int c0 = 0; c0 < R.n_cols; c0 += 16) {
+                uint32_t r[16];
+                rs::tmem_ld_32x32b_x16(taddr + c0, r);
+                rs::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(crow + c0 + j, __uint_as_float(r[j]));
+            }
+            if (R.bias) {
+                uint32_t r[8];
+                rs::tmem_ld_32x32b_x8(taddr + 256, r);
+                rs::tmem_ld_wait();
+                atomicAdd(R.bias + row, __uint_as_float(r[0]));
+            }
+            rs::tc_fence_before();
+        }
+        if (i1 > i0) acc_phase ^= 1;
+        __syncthreads();
+        rs::tc_fence_after();
+    }
+    rs::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) rs::tmem_dealloc<512>(tmem_base);
+}
+
 int g_sms = 0;
 int num_sms() {
     if (g_sms == 0) {
@@ -339,6 +469,51 @@ extern "C" int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mc
     RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int items = p.m_tiles * p.splits;
     blk_gemm_tn_kernel<<<items < num_sms() ? items : num_sms(), NUM_THREADS, smem, stream>>>(p);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// One launch for all weight / bias gradients of a layer.  Per role r < n_roles (HOST arrays of length n_roles):
+// a_mchunk[r], B[r] (tile-major pointer), b_cols[r], b_chunk0[r], n_cols[r] (multiple of 16, <= 256), b_shift[r] in {-1,0,1},
+// C[r] (fp32, 128 x n_cols[r], leading dimension ldc[r]), bias[r] (128 floats or NULL).  Outputs are ACCUMULATED into.
+extern "C" int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_roles, const int* a_mchunk,
+                            const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols,
+                            const int* b_shift, float* const* C, const int64_t* ldc, float* const* bias, int tiles, int T,
+                            void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(dG && ones_block && a_mchunk && B && b_cols && b_chunk0 && n_cols && b_shift && C && ldc && bias,
+               "rs_blk_wgrad: null pointer");
+    RS_REQUIRE(n_roles >= 1 && n_roles <= WG_MAX_ROLES, "rs_blk_wgrad: 1 <= n_roles <= %d", WG_MAX_ROLES);
+    const long long total = (long long)tiles * T;
+    if (total == 0) return 0;
+    RS_REQUIRE(total < (1ll << 31) && a_cols % 8 == 0, "rs_blk_wgrad: bad shape");
+    WgParams p = {};
+    p.A = static_cast<const uint8_t*>(dG); p.a_block_bytes = a_cols * 256;
+    p.ones = static_cast<const uint8_t*>(ones_block);
+    p.n_roles = n_roles; p.tiles = tiles; p.T = T; p.Tp = T + 2;
+    int max_n = 16;
+    for (int r = 0; r < n_roles; ++r) {
+        RS_REQUIRE(a_mchunk[r] >= 0 && (a_mchunk[r] + 16) * 8 <= a_cols, "rs_blk_wgrad: role %d columns outside dG", r);
+        RS_REQUIRE(n_cols[r] >= 16 && n_cols[r] <= 256 && n_cols[r] % 16 == 0, "rs_blk_wgrad: role %d n_cols", r);
+        RS_REQUIRE(b_chunk0[r] * 8 + n_cols[r] <= b_cols[r] && B[r] && C[r], "rs_blk_wgrad: role %d B/C", r);
+        RS_REQUIRE(b_shift[r] >= -1 && b_shift[r] <= 1, "rs_blk_wgrad: role %d shift", r);
+        WgRole& R = p.role[r];
+        R.a_mchunk = a_mchunk[r]; R.B = static_cast<const uint8_t*>(B[r]); R.b_block_bytes = b_cols[r] * 256;
+        R.b_chunk0 = b_chunk0[r]; R.n_cols = n_cols[r]; R.b_shift = b_shift[r]; R.C = C[r]; R.ldc = ldc[r]; R.bias = bias[r];
+        if (n_cols[r] > max_n) max_n = n_cols[r];
+    }
+    p.max_b_bytes = max_n * 256;
+    int splits = num_sms() / n_roles;
+    if (splits < 1) splits = 1;
+    if (splits > total) splits = (int)total;
+    p.blocks_per_split = (int)((total + splits - 1) / splits);
+    p.splits = (int)((total + p.blocks_per_split - 1) / p.blocks_per_split);
+    const int smem = 2 * (2 * PIECE_BYTES + p.max_b_bytes) + 2 * CHUNK_BYTES + 256;
+    RS_CUDA_OK(cudaFuncSetAttribute(blk_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int items = n_roles * p.splits;
+    blk_wgrad_kernel<<<items < num_sms() ? items : num_sms(), NUM_THREADS, smem, stream>>>(p);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -143,6 +143,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
             }
             __syncwarp();
         }
+    } else if (warp == 1) {
+        // ===================== L2 prefetcher: pulls the projection block of step+2 towards the SM =====================
+        if (lane == 0 && p.P) {
+            for (int step = 0; step < T; ++step) {
+                const int t = dir ? (T - 1 - step) : step;
+                const long long blk = (long long)tile * (T + 2) + t + 1;
+                rs::l2_prefetch(p.P + blk * p.p_block_bytes + (long long)(dir * 48) * CHUNK, 48 * CHUNK);
+                if (step >= 3) {                       // stay about three steps ahead of the epilogue warps
+                    rs::mbar_wait(h_ready, (step - 3) & 1);
+                }
+            }
+        }
     } else if (warp >= 2) {
         // ===================== epilogue: gates, blend, stores =====================
         const int ew = warp - 2;
@@ -168,54 +180,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                 for (int c = 0; c < 4; ++c)
                     if (c < p.I) xin[c] = __ldg(xrow + (long long)t * p.I + c);
             }
-            // input-side pre-activations of the first sub-chunk are fetched before waiting for the tensor core
-            uint4 pv[6];
-            if (pblk) {
+            // input-side pre-activations: 8 units (one 16-byte chunk per gate) per group, fetched one group ahead;
+            // the first group of a step is requested before waiting for the tensor core
+            uint4 pv[3];
+            auto load_p = [&](int grp) {      // grp = 0..7: units half*64 + grp*8 ..
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    pv[2 * g] = ldg16(pblk + (long long)(g * 16 + half * 8) * CHUNK);
-                    pv[2 * g + 1] = ldg16(pblk + (long long)(g * 16 + half * 8 + 1) * CHUNK);
-                }
-            }
+                for (int g = 0; g < 3; ++g) pv[g] = ldg16(pblk + (long long)(g * 16 + half * 8 + grp) * CHUNK);
+            };
+            if (pblk) load_p(0);
             rs::mbar_wait(acc_full, step & 1);
             rs::tc_fence_after();
-#pragma unroll 1
-            for (int sc = 0; sc < 4; ++sc) {
-                const int u0 = half * 64 + sc * 16;
-                uint32_t ar[16], az[16], an[16];
-                rs::tmem_ld_32x32b_x16(taddr + u0, ar);
-                rs::tmem_ld_32x32b_x16(taddr + 128 + u0, az);
-                rs::tmem_ld_32x32b_x16(taddr + 256 + u0, an);
-                float pr[16], pz[16], pn[16], ho[16];
-                if (pblk) {
-                    unpack8(pv[0], pr); unpack8(pv[1], pr + 8);
-                    unpack8(pv[2], pz); unpack8(pv[3], pz + 8);
-                    unpack8(pv[4], pn); unpack8(pv[5], pn + 8);
-                    if (sc < 3) {       // prefetch the next sub-chunk
 #pragma unroll
-                        for (int g = 0; g < 3; ++g) {
-                            pv[2 * g] = ldg16(pblk + (long long)(g * 16 + half * 8 + 2 * (sc + 1)) * CHUNK);
-                            pv[2 * g + 1] = ldg16(pblk + (long long)(g * 16 + half * 8 + 2 * (sc + 1) + 1) * CHUNK);
-                        }
-                    }
+            for (int grp = 0; grp < 8; ++grp) {
+                const int u0 = half * 64 + grp * 8;
+                uint32_t ar[8], az[8], an[8];
+                rs::tmem_ld_32x32b_x8(taddr + u0, ar);
+                rs::tmem_ld_32x32b_x8(taddr + 128 + u0, az);
+                rs::tmem_ld_32x32b_x8(taddr + 256 + u0, an);
+                float pr[8], pz[8], pn[8], ho[8];
+                if (pblk) {
+                    unpack8(pv[0], pr); unpack8(pv[1], pz); unpack8(pv[2], pn);
+                    if (grp < 7) load_p(grp + 1);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         const float4 wr = wx_s[u0 + j], wz = wx_s[H + u0 + j], wn = wx_s[2 * H + u0 + j];
                         pr[j] = fmaf(wr.z, xin[2], fmaf(wr.y, xin[1], fmaf(wr.x, xin[0], wr.w)));
                         pz[j] = fmaf(wz.z, xin[2], fmaf(wz.y, xin[1], fmaf(wz.x, xin[0], wz.w)));
                         pn[j] = fmaf(wn.z, xin[2], fmaf(wn.y, xin[1], fmaf(wn.x, xin[0], wn.w)));
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {       // fp32 h_{t-1}: the blend must not re-round the state every step
-                    const float4 v = *reinterpret_cast<const float4*>(h32_row + (u0 / 4 + j) * CHUNK);
-                    ho[4 * j] = v.x; ho[4 * j + 1] = v.y; ho[4 * j + 2] = v.z; ho[4 * j + 3] = v.w;
+                {   // fp32 h_{t-1}: the blend must not re-round the state every step
+                    const float4 v0 = *reinterpret_cast<const float4*>(h32_row + (u0 / 4) * CHUNK);
+                    const float4 v1 = *reinterpret_cast<const float4*>(h32_row + (u0 / 4 + 1) * CHUNK);
+                    ho[0] = v0.x; ho[1] = v0.y; ho[2] = v0.z; ho[3] = v0.w; ho[4] = v1.x; ho[5] = v1.y; ho[6] = v1.z; ho[7] = v1.w;
                 }
                 rs::tmem_ld_wait();
-                float hv[16], rv[16], zv[16], nv[16], hnv[16];
+                float hv[8], rv[8], zv[8], nv[8], hnv[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const float r = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(ar[j]) + pr[j])), 0.5f);
                     const float z = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(az[j]) + pz[j])), 0.5f);
                     const float hn = __uint_as_float(an[j]) + bhn_s[u0 + j];
@@ -223,29 +226,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                     hv[j] = fmaf(z, ho[j] - n, n);
                     rv[j] = r; zv[j] = z; nv[j] = n; hnv[j] = hn;
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(h32_row + (u0 / 4 + j) * CHUNK) = make_float4(hv[4 * j], hv[4 * j + 1], hv[4 * j + 2], hv[4 * j + 3]);
-                const uint4 o0 = pack8(hv), o1 = pack8(hv + 8);
+                *reinterpret_cast<float4*>(h32_row + (u0 / 4) * CHUNK) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<float4*>(h32_row + (u0 / 4 + 1) * CHUNK) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                const uint4 o0 = pack8(hv);
                 *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK) = o0;      // next step's A operand, in place
-                *reinterpret_cast<uint4*>(a_row + (u0 / 8 + 1) * CHUNK) = o1;
                 stg16(oblk + (long long)(u0 / 8) * CHUNK, o0);
-                stg16(oblk + (long long)(u0 / 8 + 1) * CHUNK, o1);
                 if (gblk) {
                     stg16(gblk + (long long)(0 * 16 + u0 / 8) * CHUNK, pack8h(rv));
-                    stg16(gblk + (long long)(0 * 16 + u0 / 8 + 1) * CHUNK, pack8h(rv + 8));
                     stg16(gblk + (long long)(1 * 16 + u0 / 8) * CHUNK, pack8h(zv));
-                    stg16(gblk + (long long)(1 * 16 + u0 / 8 + 1) * CHUNK, pack8h(zv + 8));
                     stg16(gblk + (long long)(2 * 16 + u0 / 8) * CHUNK, pack8h(nv));
-                    stg16(gblk + (long long)(2 * 16 + u0 / 8 + 1) * CHUNK, pack8h(nv + 8));
                     stg16(gblk + (long long)(3 * 16 + u0 / 8) * CHUNK, pack8h(hnv));
-                    stg16(gblk + (long long)(3 * 16 + u0 / 8 + 1) * CHUNK, pack8h(hnv + 8));
                 }
                 if (step == T - 1 && live) {
                     float* hn_out = p.h_n + ((long long)dir * p.B + b) * H + u0;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(hn_out + j) = make_float4(hv[j], hv[j + 1], hv[j + 2], hv[j + 3]);
+                    *reinterpret_cast<float4*>(hn_out) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    *reinterpret_cast<float4*>(hn_out + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
                 }
             }
             rs::fence_proxy_async();        // h_t written with ordinary stores -> visible to tcgen05.mma
@@ -313,41 +308,87 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
                 for (int k = 0; k < 24; ++k) {
                     const uint64_t da = rs::umma_desc_noswz(a_addr + k * 2 * CHUNK, CHUNK, 128);
                     const uint64_t db = rs::umma_desc_noswz(w_addr + k * 2 * CHUNK, CHUNK, 128);
-                    rs::tc_mma_bf16(tmem_base, da, db, idesc, k != 0);
+                    rs::tc_mma_bf16(tmem_base, da, db, idesc, 1u);   // accumulates ONTO the z (.) dh carry stored in TMEM
                 }
                 rs::tc_commit(acc_full);
             }
             __syncwarp();
         }
-    } else if (warp >= 2) {
+    } else if (warp == 1) {
+        // L2 prefetcher: saved gates, h_{prev} and d_out of the step two ahead (contiguous tile-major ranges)
+        if (lane == 0) {
+            for (int s = 0; s < T; ++s) {
+                const int fstep = T - 1 - s;
+                const int t = dir ? (T - 1 - fstep) : fstep;
+                const int t_prev = dir ? t + 1 : t - 1;
+                const long long blk = (long long)tile * (T + 2) + t + 1;
+                const long long blk_prev = (long long)tile * (T + 2) + t_prev + 1;
+                rs::l2_prefetch(p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK), 64 * CHUNK);
+                rs::l2_prefetch(p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16) * CHUNK, 16 * CHUNK);
+                if (p.d_out) rs::l2_prefetch(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16) * CHUNK, 16 * CHUNK);
+                if (s >= 3) rs::mbar_wait(a_ready, (s - 3) & 1);
+            }
+        }
+    } else {
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
         const int row = q * 32 + lane;
         const long long b = (long long)tile * 128 + row;
         const bool live = b < p.B;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
         uint8_t* a_row = a_s + row * 16;
-        float carry[64];                                // z (.) dh of the step processed before (fp32, registers)
+        // the carry z (.) dh lives in the TMEM accumulator; it starts as d_h_n
 #pragma unroll
-        for (int j = 0; j < 64; ++j) carry[j] = 0.0f;
-        if (p.d_h_n && live) {
-            const float* src = p.d_h_n + ((long long)dir * p.B + b) * H + half * 64;
+        for (int sc = 0; sc < 4; ++sc) {
+            uint32_t init[16];
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + j));
-                carry[j] = v.x; carry[j + 1] = v.y; carry[j + 2] = v.z; carry[j + 3] = v.w;
+            for (int j = 0; j < 16; ++j) init[j] = 0u;
+            if (p.d_h_n && live) {
+                const float* src = p.d_h_n + ((long long)dir * p.B + b) * H + half * 64 + sc * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + j));
+                    init[j] = __float_as_uint(v.x); init[j + 1] = __float_as_uint(v.y);
+                    init[j + 2] = __float_as_uint(v.z); init[j + 3] = __float_as_uint(v.w);
+                }
             }
+            rs::tmem_st_32x32b_x16(taddr + sc * 16, init);
         }
-        for (int s = 0; s < T; ++s) {                   // s-th reverse step = forward position T-1-s
+        rs::tmem_st_wait();
+
+        // raw 16-byte pieces of one sub-chunk (16 units): r, z, n, hn (fp16), h_prev, d_out (bf16), two chunks each
+        uint4 raw[12];
+        auto load_raw = [&](int s, int sc) {
             const int fstep = T - 1 - s;
             const int t = dir ? (T - 1 - fstep) : fstep;
-            const int t_prev = dir ? t + 1 : t - 1;     // time row of h_{prev}; the pad rows hold the zero initial state
+            const int t_prev = dir ? t + 1 : t - 1;
             const long long blk = (long long)tile * (T + 2) + t + 1;
             const long long blk_prev = (long long)tile * (T + 2) + t_prev + 1;
             const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK) + row * 16;
             const uint8_t* hblk = p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16) * CHUNK + row * 16;
-            const uint8_t* doblk = p.d_out ? p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16) * CHUNK + row * 16 : nullptr;
+            const int c0 = half * 8 + sc * 2;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                raw[2 * g] = ldg16(gblk + (long long)(g * 16 + c0) * CHUNK);
+                raw[2 * g + 1] = ldg16(gblk + (long long)(g * 16 + c0 + 1) * CHUNK);
+            }
+            raw[8] = ldg16(hblk + (long long)c0 * CHUNK);
+            raw[9] = ldg16(hblk + (long long)(c0 + 1) * CHUNK);
+            if (p.d_out) {
+                const uint8_t* doblk = p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16) * CHUNK + row * 16;
+                raw[10] = ldg16(doblk + (long long)c0 * CHUNK);
+                raw[11] = ldg16(doblk + (long long)(c0 + 1) * CHUNK);
+            } else {
+                raw[10] = make_uint4(0, 0, 0, 0);
+                raw[11] = make_uint4(0, 0, 0, 0);
+            }
+        };
+        load_raw(0, 0);
+        for (int s = 0; s < T; ++s) {                   // s-th reverse step = forward position T-1-s
+            const int fstep = T - 1 - s;
+            const int t = dir ? (T - 1 - fstep) : fstep;
+            const long long blk = (long long)tile * (T + 2) + t + 1;
             uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 64) * CHUNK + row * 16;
             if (s > 0) {
                 rs::mbar_wait(acc_full, (s - 1) & 1);
@@ -355,47 +396,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
             }
 #pragma unroll
             for (int sc = 0; sc < 4; ++sc) {
-                const int c0 = half * 8 + sc * 2;       // first of the two 8-unit chunks of this sub-chunk
+                const int c0 = half * 8 + sc * 2;
                 uint32_t acc[16];
-                if (s > 0) rs::tmem_ld_32x32b_x16(taddr + half * 64 + sc * 16, acc);
-                float r[16], z[16], n[16], hn[16], hp[16], dout[16];
-                unpack8h(ldg16(gblk + (long long)(0 * 16 + c0) * CHUNK), r);  unpack8h(ldg16(gblk + (long long)(0 * 16 + c0 + 1) * CHUNK), r + 8);
-                unpack8h(ldg16(gblk + (long long)(1 * 16 + c0) * CHUNK), z);  unpack8h(ldg16(gblk + (long long)(1 * 16 + c0 + 1) * CHUNK), z + 8);
-                unpack8h(ldg16(gblk + (long long)(2 * 16 + c0) * CHUNK), n);  unpack8h(ldg16(gblk + (long long)(2 * 16 + c0 + 1) * CHUNK), n + 8);
-                unpack8h(ldg16(gblk + (long long)(3 * 16 + c0) * CHUNK), hn); unpack8h(ldg16(gblk + (long long)(3 * 16 + c0 + 1) * CHUNK), hn + 8);
-                unpack8(ldg16(hblk + (long long)c0 * CHUNK), hp);            unpack8(ldg16(hblk + (long long)(c0 + 1) * CHUNK), hp + 8);
-                if (doblk) {
-                    unpack8(ldg16(doblk + (long long)c0 * CHUNK), dout);     unpack8(ldg16(doblk + (long long)(c0 + 1) * CHUNK), dout + 8);
-                }
-                if (s > 0) rs::tmem_ld_wait();
-                float gr[16], gz[16], gn[16], ghn[16];
+                rs::tmem_ld_32x32b_x16(taddr + sc * 16, acc);
+                uint4 cur[12];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float dh = carry[sc * 16 + j];
-                    if (s > 0) dh += __uint_as_float(acc[j]);
-                    if (doblk) dh += dout[j];
-                    const float dn = dh * (1.0f - z[j]);
-                    const float dz = dh * (hp[j] - n[j]);
-                    gn[j] = dn * (1.0f - n[j] * n[j]);
-                    gz[j] = dz * z[j] * (1.0f - z[j]);
-                    ghn[j] = gn[j] * r[j];
-                    gr[j] = gn[j] * hn[j] * r[j] * (1.0f - r[j]);
-                    carry[sc * 16 + j] = dh * z[j];
+                for (int i = 0; i < 12; ++i) cur[i] = raw[i];
+                if (sc < 3) load_raw(s, sc + 1);                    // next sub-chunk of this step
+                else if (s + 1 < T) load_raw(s + 1, 0);             // first sub-chunk of the next step (before its MMA wait)
+                rs::tmem_ld_wait();
+                uint32_t carry[16];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {                    // two groups of 8 units keep the live set small
+                    float r[8], z[8], n[8], hn[8], hp[8], dout[8];
+                    unpack8h(cur[0 + hf], r); unpack8h(cur[2 + hf], z); unpack8h(cur[4 + hf], n); unpack8h(cur[6 + hf], hn);
+                    unpack8(cur[8 + hf], hp); unpack8(cur[10 + hf], dout);
+                    float gr[8], gz[8], gn[8], ghn[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dh = __uint_as_float(acc[hf * 8 + j]) + dout[j];
+                        const float dn = dh * (1.0f - z[j]);
+                        const float dz = dh * (hp[j] - n[j]);
+                        gn[j] = dn * (1.0f - n[j] * n[j]);
+                        gz[j] = dz * z[j] * (1.0f - z[j]);
+                        ghn[j] = gn[j] * r[j];
+                        gr[j] = gn[j] * hn[j] * r[j] * (1.0f - r[j]);
+                        carry[hf * 8 + j] = __float_as_uint(dh * z[j]);
+                    }
+                    const uint4 vr = pack8(gr), vz = pack8(gz), vn = pack8(gn), vh = pack8(ghn);
+                    // A operand of the dh matvec: K order r | z | hn
+                    *reinterpret_cast<uint4*>(a_row + (0 * 16 + c0 + hf) * CHUNK) = vr;
+                    *reinterpret_cast<uint4*>(a_row + (1 * 16 + c0 + hf) * CHUNK) = vz;
+                    *reinterpret_cast<uint4*>(a_row + (2 * 16 + c0 + hf) * CHUNK) = vh;
+                    stg16(dgblk + (long long)(0 * 16 + c0 + hf) * CHUNK, vr);
+                    stg16(dgblk + (long long)(1 * 16 + c0 + hf) * CHUNK, vz);
+                    stg16(dgblk + (long long)(2 * 16 + c0 + hf) * CHUNK, vn);
+                    stg16(dgblk + (long long)(3 * 16 + c0 + hf) * CHUNK, vh);
                 }
-                const uint4 vr0 = pack8(gr), vr1 = pack8(gr + 8), vz0 = pack8(gz), vz1 = pack8(gz + 8);
-                const uint4 vn0 = pack8(gn), vn1 = pack8(gn + 8), vh0 = pack8(ghn), vh1 = pack8(ghn + 8);
-                // A operand of the dh matvec: K order r | z | hn
-                *reinterpret_cast<uint4*>(a_row + (0 * 16 + c0) * CHUNK) = vr0;
-                *reinterpret_cast<uint4*>(a_row + (0 * 16 + c0 + 1) * CHUNK) = vr1;
-                *reinterpret_cast<uint4*>(a_row + (1 * 16 + c0) * CHUNK) = vz0;
-                *reinterpret_cast<uint4*>(a_row + (1 * 16 + c0 + 1) * CHUNK) = vz1;
-                *reinterpret_cast<uint4*>(a_row + (2 * 16 + c0) * CHUNK) = vh0;
-                *reinterpret_cast<uint4*>(a_row + (2 * 16 + c0 + 1) * CHUNK) = vh1;
-                stg16(dgblk + (long long)(0 * 16 + c0) * CHUNK, vr0); stg16(dgblk + (long long)(0 * 16 + c0 + 1) * CHUNK, vr1);
-                stg16(dgblk + (long long)(1 * 16 + c0) * CHUNK, vz0); stg16(dgblk + (long long)(1 * 16 + c0 + 1) * CHUNK, vz1);
-                stg16(dgblk + (long long)(2 * 16 + c0) * CHUNK, vn0); stg16(dgblk + (long long)(2 * 16 + c0 + 1) * CHUNK, vn1);
-                stg16(dgblk + (long long)(3 * 16 + c0) * CHUNK, vh0); stg16(dgblk + (long long)(3 * 16 + c0 + 1) * CHUNK, vh1);
+                rs::tmem_st_32x32b_x16(taddr + sc * 16, carry);     // the next MMA accumulates dGh . W_hh onto it
             }
+            rs::tmem_st_wait();
             rs::fence_proxy_async();
             rs::tc_fence_before();
             __syncwarp();

@@ -173,13 +173,15 @@ class GRULayerFn(torch.autograd.Function):
             del P
         ctx.dims = (B, T, Il, H)
         ctx.mask = mask
-        ctx.saved = (out, gates, xin, padded_in, w_ih_cat, w_hh_cat)
+        ctx.padded_in_saved = bool(padded_in)
+        ctx.save_for_backward(out, gates, xin, w_ih_cat, w_hh_cat)   # outputs must go through save_for_backward (no ref cycle)
         return out, h_n
 
     @staticmethod
     def backward(ctx, d_out, d_h_n):
         B, T, Il, H = ctx.dims
-        out, gates, xin, padded_in, w_ih_cat, w_hh_cat = ctx.saved
+        out, gates, xin, w_ih_cat, w_hh_cat = ctx.saved_tensors
+        padded_in = ctx.padded_in_saved
         if gates is None:
             raise RuntimeError("GRULayerFn: forward ran without saving activations (nothing required grad)")
         dev = out.device

@@ -36,6 +36,25 @@ def _tn(A, a_cols, mchunks, rows, Bm, b_cols, b_chunk0, n_cols, shift, bcast, C,
               b_chunk0, n_cols, shift, int(bcast), _p(C), ldc, tiles, T, st)
 
 
+def _wgrad(dG, a_cols, ones, roles, tiles, T, st):
+    """roles: list of (a_mchunk, B tensor, b_cols, b_chunk0, n_cols, b_shift, C tensor view, ldc, bias view or None)."""
+    n = len(roles)
+    vp = ctypes.c_void_p * n
+    i64 = ctypes.c_int64 * n
+    a_m = L.int_array([r[0] for r in roles])
+    Bp = vp(*[r[1].data_ptr() for r in roles])
+    b_cols = i64(*[r[2] for r in roles])
+    b_c0 = L.int_array([r[3] for r in roles])
+    n_cols = L.int_array([r[4] for r in roles])
+    shift = L.int_array([r[5] for r in roles])
+    Cp = vp(*[r[6].data_ptr() for r in roles])
+    ldc = i64(*[r[7] for r in roles])
+    bias = vp(*[(r[8].data_ptr() if r[8] is not None else None) for r in roles])
+    adr = ctypes.addressof
+    _lib.call("rs_blk_wgrad", _p(dG), a_cols, _p(ones), n, adr(a_m), adr(Bp), adr(b_cols), adr(b_c0), adr(n_cols), adr(shift),
+              adr(Cp), adr(ldc), adr(bias), tiles, T, st)
+
+
 _ONES = {}
 
 
@@ -105,13 +124,15 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 saved_in = X
         ctx.meta = (padded_in, B, T, Il)
         ctx.mask = mask
-        ctx.saved = (out, gates, saved_in, w_ih_cat, w_hh_cat)
+        # save_for_backward (not ctx attributes): `out` is an OUTPUT of this node; holding it in a plain attribute
+        # would create a reference cycle node -> out -> grad_fn -> node and keep gigabytes alive until the cycle GC runs
+        ctx.save_for_backward(out, gates, saved_in, w_ih_cat, w_hh_cat)
         return out, h_n
 
     @staticmethod
     def backward(ctx, d_out, d_h_n):
         padded_in, B, T, Il = ctx.meta
-        out, gates, saved_in, w_ih_cat, w_hh_cat = ctx.saved
+        out, gates, saved_in, w_ih_cat, w_hh_cat = ctx.saved_tensors
         if gates is None:
             raise RuntimeError("GRULayerBF16Fn: forward ran without saving activations (nothing required grad)")
         dev = out.device
@@ -127,39 +148,36 @@ class GRULayerBF16Fn(torch.autograd.Function):
             dG[:, T + 1].zero_()
             with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
                 _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), B, T, st)
-            # hidden-side weight gradients: dG(t') pairs with h(t'-1) (forward) / h(t'+1) (reverse)
+            # ALL weight / bias gradients of the layer in one fused pass over dG (12 roles, see csrc/gemm_blk.cu):
+            #   ih roles (dir, g in r,z,n): dG block ^T . X            -> dW_ih rows, bias sums of r, z, n
+            #   hh roles (dir, g in r,z,hn): dG block ^T . h(t' -/+ 1) -> dW_hh rows, bias sum of hn
             dW_hh = torch.zeros(2, 3 * H, H, device=dev)
-            with ktime("blk_gemm_tn_kernel(wgrad)", 2.0 * tiles * L.TILE * T * 6 * H * H):
-                for d in (0, 1):
-                    _tn(dG, 8 * H, [d * 64 + 0, d * 64 + 16, d * 64 + 48], [0, H, 2 * H], out, 2 * H, d * 16, H,
-                        -1 if d == 0 else 1, False, dW_hh[d], H, tiles, T, st)
-            # bias gradients: column sums of the eight gate blocks (ones column as the B operand)
-            sums = torch.zeros(8 * H, 16, device=dev)
-            with ktime("blk_gemm_tn_kernel(bias)", 2.0 * tiles * L.TILE * T * 8 * H * 16):
-                _tn(dG, 8 * H, [16 * i for i in range(8)], [H * i for i in range(8)], _ones_block(dev), 16, 0, 16, 0, True,
-                    sums, 16, tiles, T, st)
-            s = sums[:, 0].view(2, 4, H)
-            db_ih = s[:, :3].reshape(2, 3 * H)
-            db_hh = torch.cat([s[:, :2].reshape(2, 2 * H), s[:, 3]], 1)
-            # input-side weight gradients
-            d_xin = None
+            sums = torch.zeros(2, 4, H, device=dev)              # per direction: r | z | n | hn column sums of dG
             if not padded_in:
-                x = saved_in
                 xa = torch.zeros(B, T, 16, device=dev)
-                xa[:, :, :Il] = x
-                xa_tm = L.to_tile_major(xa)
-                dW = torch.zeros(6 * H, 16, device=dev)
-                with ktime("blk_gemm_tn_kernel(wgrad)", 2.0 * tiles * L.TILE * T * 6 * H * 16):
-                    _tn(dG, 8 * H, [d * 64 + g * 16 for d in (0, 1) for g in (0, 1, 2)], [H * i for i in range(6)], xa_tm, 16, 0,
-                        16, 0, False, dW, 16, tiles, T, st)
-                dW_ih = dW[:, :Il].contiguous()
+                xa[:, :, :Il] = saved_in
+                Xb, xb_cols, n_ih = L.to_tile_major(xa), 16, 16
             else:
+                Xb, xb_cols, n_ih = saved_in, Il, Il
+            if n_ih > 256:
+                raise _lib.RoomSlamError("bf16 mode: layer input wider than 256 columns is not supported")
+            dW_ih_buf = torch.zeros(6 * H, n_ih, device=dev)
+            roles = []
+            for d in (0, 1):
+                for g in (0, 1, 2):                                # r, z, n against the layer input
+                    roles.append((d * 64 + g * 16, Xb, xb_cols, 0, n_ih, 0, dW_ih_buf[(d * 3 + g) * H:], n_ih, sums[d, g]))
+                for gi, g in enumerate((0, 1, 3)):                 # r, z, hn against the shifted hidden state
+                    roles.append((d * 64 + g * 16, out, 2 * H, d * 16, H, -1 if d == 0 else 1, dW_hh[d, gi * H:], H,
+                                  sums[d, 3] if g == 3 else None))
+            flops = 2.0 * tiles * L.TILE * T * (6 * H * n_ih + 6 * H * H + 8 * H * 16)
+            with ktime("blk_wgrad_kernel", flops):
+                _wgrad(dG, 8 * H, _ones_block(dev), roles, tiles, T, st)
+            db_ih = sums[:, :3].reshape(2, 3 * H)
+            db_hh = torch.cat([sums[:, :2].reshape(2, 2 * H), sums[:, 3]], 1)
+            dW_ih = dW_ih_buf[:, :Il].contiguous() if not padded_in else dW_ih_buf
+            d_xin = None
+            if padded_in:
                 X = saved_in
-                dW_ih = torch.zeros(6 * H, Il, device=dev)
-                with ktime("blk_gemm_tn_kernel(wgrad)", 2.0 * tiles * L.TILE * T * 6 * H * Il):
-                    for c0 in range(0, Il, 256):
-                        _tn(dG, 8 * H, [d * 64 + g * 16 for d in (0, 1) for g in (0, 1, 2)], [H * i for i in range(6)], X, Il,
-                            c0 // 8, min(256, Il - c0), 0, False, dW_ih[:, c0:], Il, tiles, T, st)
                 if ctx.needs_input_grad[0]:
                     dX = torch.empty(tiles, T + 2, Il // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
                     wt = L.tile_weight_nt(w_ih_cat.t().contiguous())               # [Il/128][12][8][128][8]
