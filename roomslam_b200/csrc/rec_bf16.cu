@@ -14,6 +14,7 @@
 // Backward, per step (reverse time):  dh_{t-1} = z (.) dh_t + dGh_t[128 x 384] . W_hh  on tcgen05, with W_hh^T resident
 //   in shared memory, dGh_t written by the epilogue warps as the A operand, the z (.) dh carry kept in fp32 registers.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/roomslam_b200.h"
@@ -39,6 +40,7 @@ struct FwdParams {
     uint8_t* gates;                         // [tiles][T][2][64][128][8] fp16 (private to fwd/bwd) or NULL
     float* h_n;                             // [2][B][H]
     int B, T;
+    int pf_dist;                            // L2 prefetch distance in steps (0 = off)
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -145,13 +147,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
         }
     } else if (warp == 1) {
         // ===================== L2 prefetcher: pulls the projection block of step+2 towards the SM =====================
-        if (lane == 0 && p.P) {
+        if (lane == 0 && p.P && p.pf_dist > 0) {
             for (int step = 0; step < T; ++step) {
                 const int t = dir ? (T - 1 - step) : step;
                 const long long blk = (long long)tile * (T + 2) + t + 1;
                 rs::l2_prefetch(p.P + blk * p.p_block_bytes + (long long)(dir * 48) * CHUNK, 48 * CHUNK);
-                if (step >= 3) {                       // stay about three steps ahead of the epilogue warps
-                    rs::mbar_wait(h_ready, (step - 3) & 1);
+                if (step >= p.pf_dist) {               // stay pf_dist steps ahead of the epilogue warps
+                    rs::mbar_wait(h_ready, (step - p.pf_dist) & 1);
                 }
             }
         }
@@ -190,13 +192,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
             if (pblk) load_p(0);
             rs::mbar_wait(acc_full, step & 1);
             rs::tc_fence_after();
+            uint32_t ar[8], az[8], an[8];
+            rs::tmem_ld_32x32b_x8(taddr + half * 64, ar);
+            rs::tmem_ld_32x32b_x8(taddr + 128 + half * 64, az);
+            rs::tmem_ld_32x32b_x8(taddr + 256 + half * 64, an);
 #pragma unroll
             for (int grp = 0; grp < 8; ++grp) {
                 const int u0 = half * 64 + grp * 8;
-                uint32_t ar[8], az[8], an[8];
-                rs::tmem_ld_32x32b_x8(taddr + u0, ar);
-                rs::tmem_ld_32x32b_x8(taddr + 128 + u0, az);
-                rs::tmem_ld_32x32b_x8(taddr + 256 + u0, an);
                 float pr[8], pz[8], pn[8], ho[8];
                 if (pblk) {
                     unpack8(pv[0], pr); unpack8(pv[1], pz); unpack8(pv[2], pn);
@@ -216,12 +218,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                     ho[0] = v0.x; ho[1] = v0.y; ho[2] = v0.z; ho[3] = v0.w; ho[4] = v1.x; ho[5] = v1.y; ho[6] = v1.z; ho[7] = v1.w;
                 }
                 rs::tmem_ld_wait();
+                float gr_[8], gz_[8], gn_[8];        // this group's accumulator values; the registers are then reloaded
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { gr_[j] = __uint_as_float(ar[j]); gz_[j] = __uint_as_float(az[j]); gn_[j] = __uint_as_float(an[j]); }
+                if (grp < 7) {                      // TMEM loads of the next group fly while this group is computed
+                    rs::tmem_ld_32x32b_x8(taddr + u0 + 8, ar);
+                    rs::tmem_ld_32x32b_x8(taddr + 128 + u0 + 8, az);
+                    rs::tmem_ld_32x32b_x8(taddr + 256 + u0 + 8, an);
+                }
                 float hv[8], rv[8], zv[8], nv[8], hnv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float r = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(ar[j]) + pr[j])), 0.5f);
-                    const float z = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(az[j]) + pz[j])), 0.5f);
-                    const float hn = __uint_as_float(an[j]) + bhn_s[u0 + j];
+                    const float r = fmaf(0.5f, tanh_fast(0.5f * (gr_[j] + pr[j])), 0.5f);
+                    const float z = fmaf(0.5f, tanh_fast(0.5f * (gz_[j] + pz[j])), 0.5f);
+                    const float hn = gn_[j] + bhn_s[u0 + j];
                     const float n = tanh_fast(fmaf(r, hn, pn[j]));
                     hv[j] = fmaf(z, ho[j] - n, n);
                     rv[j] = r; zv[j] = z; nv[j] = n; hnv[j] = hn;
@@ -263,6 +273,7 @@ struct BwdParams {
     const uint8_t* WhhT;                                 // [2][48][128][8] bf16: rows = h index, K = (r | z | hn) gate rows
     uint8_t* dG; long long dg_block_bytes;               // tile-major C = 8H: [dir][r | z | n | hn][H]
     int B, T;
+    int pf_dist;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdParams p) {
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
         }
     } else if (warp == 1) {
         // L2 prefetcher: saved gates, h_{prev} and d_out of the step two ahead (contiguous tile-major ranges)
-        if (lane == 0) {
+        if (lane == 0 && p.pf_dist > 0) {
             for (int s = 0; s < T; ++s) {
                 const int fstep = T - 1 - s;
                 const int t = dir ? (T - 1 - fstep) : fstep;
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
                 rs::l2_prefetch(p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK), 64 * CHUNK);
                 rs::l2_prefetch(p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16) * CHUNK, 16 * CHUNK);
                 if (p.d_out) rs::l2_prefetch(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16) * CHUNK, 16 * CHUNK);
-                if (s >= 3) rs::mbar_wait(a_ready, (s - 3) & 1);
+                if (s >= p.pf_dist) rs::mbar_wait(a_ready, (s - p.pf_dist) & 1);
             }
         }
     } else {
@@ -447,6 +458,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
     if (warp == 0) rs::tmem_dealloc<128>(tmem_base);
 }
 
+// Tuning knobs: L2 bulk-prefetch distance in steps (0 = off).  Measured at B = 8192 (tools/step_probe.py): the forward
+// kernel is fastest one step ahead (6.8 ms vs 7.4 ms off); the backward kernel is fastest WITHOUT prefetch (7.3 ms vs
+// 9.7 ms at distance 3: it already runs at ~86 % of the HBM peak, extra prefetches only get evicted and re-read).
+int pf_dist_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    int v = e ? atoi(e) : dflt;
+    if (v < 0) v = 0;
+    if (v > 64) v = 64;
+    return v;
+}
+
 }  // namespace
 
 extern "C" int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, const void* P, int64_t p_cols, const void* Whh,
@@ -468,6 +490,7 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, co
     p.Whh = static_cast<const uint8_t*>(Whh); p.b_hn = b_hn;
     p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
     p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.B = B; p.T = T;
+    p.pf_dist = pf_dist_env("RS_PF_DIST_FWD", 1);
     const int smem = W_BYTES + A_FWD_BYTES + H32_BYTES + 3 * H * 16 + H * 4 + 64;
     RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     rec_fwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
@@ -489,6 +512,7 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
     p.WhhT = static_cast<const uint8_t*>(WhhT);
     p.dG = static_cast<uint8_t*>(dG); p.dg_block_bytes = 8LL * H * 256;
     p.B = B; p.T = T;
+    p.pf_dist = pf_dist_env("RS_PF_DIST_BWD", 0);
     const int smem = W_BYTES + A_BWD_BYTES + 64;
     RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     rec_bwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
