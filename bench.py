@@ -344,8 +344,11 @@ def run_ours(args):
                         "ms_per_step": ms_heat_e2e},
                 "roofline": {"bound": "hbm", "achieved": n_tr * SEQ_LEN * 8 / (ms_kernel / 1e3) / 1e9, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": n_tr * SEQ_LEN * 8 / (ms_kernel / 1e3) / 1e9 / pk["hbm_gbs"],
-                             "traffic": None, "kernel": "heatmap_tma_kernel", "kernel_ms": ms_kernel,
-                             "algorithmic_bytes_per_point": 8, "peak_source": pk["source"]},
+                             # dram__bytes_read+write of one `ncu --set full` capture (profiles/r1_heatmap_ncu.md):
+                             # 1.648 GB for 2e8 points = 8.24 B/point, scaled to this launch's point count
+                             "traffic": int(8.24 * n_tr * SEQ_LEN), "kernel": "heatmap_tma_kernel", "kernel_ms": ms_kernel,
+                             "algorithmic_bytes_per_point": 8, "algorithmic_bytes": 8 * n_tr * SEQ_LEN,
+                             "peak_source": pk["source"] + ", burst (kernel timed alone)"},
             },
         }
         line["roofline"] = train_roofline(kernel_ms, B, pk, precision) or line["heatmap"]["roofline"]
@@ -369,6 +372,9 @@ def train_roofline(kernel_ms, B, pk, precision):
     ach = flops / (ms / 1e3) / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
             "frac": ach / pk["tflops_sustained"], "traffic": None, "kernel": name, "kernel_ms": ms, "launches": calls,
+            "algorithmic_flops": flops,
+            "note": "dominant kernel of the training step by CUDA-event time; in practice it is bound by the HBM traffic of "
+                    "saved activations (DESIGN.md 4.2), the tensor figure is the algorithmic-FLOP view SURVEY.md 8(d) asks for",
             "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)"}
 
 

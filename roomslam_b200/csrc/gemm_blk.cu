@@ -21,7 +21,7 @@ namespace {
 
 constexpr int CHUNK_BYTES = 2048;          // one 16-byte column chunk of a 128-trace block
 constexpr int PIECE_BYTES = 8 * CHUNK_BYTES;   // 64 columns x 128 traces = 16 KB
-constexpr int NT_STAGES = 4;
+constexpr int NT_STAGES_MAX = 6;           // ring depth (5 resident / 6 streaming): look-ahead that covers the L2 latency of the W pieces
 constexpr int NT_MAX_KB = 12;
 constexpr int NUM_THREADS = 192;
 
@@ -33,29 +33,39 @@ struct NtParams {
     int n_blocks, n_tiles, k_blocks;
 };
 
+constexpr int NT_THREADS = 320;            // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (2 per TMEM lane quadrant)
+constexpr int NT_MAX_N = 1024;             // bias staged in shared memory
+
 template <bool kResident>
-__global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtParams p) {
+__global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_kernel(const NtParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* a_res = smem;                                        // 4 x 16 KB (resident A block, K <= 256)
-    uint8_t* stages = smem + 4 * PIECE_BYTES;                     // NT_STAGES x (A piece | W piece)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NT_STAGES * 2 * PIECE_BYTES);
+    // resident: two A blocks (2 x 64 KB, double-buffered across blocks) + ring of W pieces (16 KB each)
+    // streaming: ring of (A piece | W piece) stages (32 KB each)
+    constexpr int kStageBytes = kResident ? PIECE_BYTES : 2 * PIECE_BYTES;
+    constexpr int NT_STAGES = kResident ? 5 : 6;
+    uint8_t* a_res = smem;
+    uint8_t* stages = smem + (kResident ? 2 * 4 * PIECE_BYTES : 0);
+    float* bias_s = reinterpret_cast<float*>(stages + NT_STAGES * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + NT_MAX_N);
     uint64_t* full_bar = bars;                       // [NT_STAGES]
     uint64_t* empty_bar = bars + NT_STAGES;          // [NT_STAGES]
     uint64_t* acc_full = bars + 2 * NT_STAGES;       // [2]
     uint64_t* acc_empty = bars + 2 * NT_STAGES + 2;  // [2]
-    uint64_t* a_full = bars + 2 * NT_STAGES + 4;     // resident A landed
-    uint64_t* a_empty = bars + 2 * NT_STAGES + 5;    // MMAs of the block retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NT_STAGES + 6);
+    uint64_t* a_full = bars + 2 * NT_STAGES + 4;     // [2] resident A block landed
+    uint64_t* a_empty = bars + 2 * NT_STAGES + 6;    // [2] MMAs of that block retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NT_STAGES + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NT_STAGES; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { rs::mbar_init(&acc_full[s], 1); rs::mbar_init(&acc_empty[s], 4); }
-        rs::mbar_init(a_full, 1);
-        rs::mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) {
+            rs::mbar_init(&acc_full[s], 1); rs::mbar_init(&acc_empty[s], 8);
+            rs::mbar_init(&a_full[s], 1);   rs::mbar_init(&a_empty[s], 1);
+        }
         rs::fence_mbar_init();
     }
     if (warp == 1) rs::tmem_alloc<256>(tmem_slot);
+    for (int i = threadIdx.x; i < p.n_tiles * 128; i += NT_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.0f;
     rs::tc_fence_before();
     __syncthreads();
     rs::tc_fence_after();
@@ -63,25 +73,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtPar
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, a_phase = 0;
+            int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t a_phase = 0;
             for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
                 const uint8_t* ablk = p.A + (long long)m * p.a_block_bytes;
                 if (kResident) {
-                    rs::mbar_wait(a_empty, a_phase ^ 1);
-                    a_phase ^= 1;
-                    rs::mbar_expect_tx(a_full, p.k_blocks * PIECE_BYTES);
+                    rs::mbar_wait(&a_empty[ab], a_phase ^ 1);
+                    rs::mbar_expect_tx(&a_full[ab], p.k_blocks * PIECE_BYTES);
                     for (int kb = 0; kb < p.k_blocks; ++kb)
-                        rs::bulk_load(a_res + kb * PIECE_BYTES, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES, a_full);
+                        rs::bulk_load(a_res + (ab * 4 + kb) * PIECE_BYTES, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES,
+                                      &a_full[ab]);
+                    if (++ab == 2) { ab = 0; a_phase ^= 1; }
                 }
                 for (int n = 0; n < p.n_tiles; ++n) {
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         rs::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = stages + stage * 2 * PIECE_BYTES;
-                        rs::mbar_expect_tx(&full_bar[stage], kResident ? PIECE_BYTES : 2 * PIECE_BYTES);
+                        uint8_t* ss = stages + stage * kStageBytes;
+                        rs::mbar_expect_tx(&full_bar[stage], kStageBytes);
                         if (!kResident)
-                            rs::bulk_load(sa, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES, &full_bar[stage]);
-                        rs::bulk_load(sa + PIECE_BYTES, p.W + ((long long)n * p.k_blocks + kb) * PIECE_BYTES, PIECE_BYTES,
-                                      &full_bar[stage]);
+                            rs::bulk_load(ss, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES, &full_bar[stage]);
+                        rs::bulk_load(ss + (kResident ? 0 : PIECE_BYTES), p.W + ((long long)n * p.k_blocks + kb) * PIECE_BYTES,
+                                      PIECE_BYTES, &full_bar[stage]);
                         if (++stage == NT_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -89,9 +100,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtPar
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = rs::umma_idesc_bf16(128, 128, 0, 0);
-        int stage = 0; uint32_t phase = 0, a_phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t a_phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
-            if (kResident) { rs::mbar_wait(a_full, a_phase); a_phase ^= 1; rs::tc_fence_after(); }
+            if (kResident) { rs::mbar_wait(&a_full[ab], a_phase); rs::tc_fence_after(); }
             for (int n = 0; n < p.n_tiles; ++n) {
                 rs::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 rs::tc_fence_after();
@@ -100,9 +111,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtPar
                     rs::mbar_wait(&full_bar[stage], phase);
                     rs::tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t ss = rs::smem_u32(stages + stage * 2 * PIECE_BYTES);
-                        const uint32_t sa = kResident ? rs::smem_u32(a_res + kb * PIECE_BYTES) : ss;
-                        const uint32_t sb = ss + PIECE_BYTES;
+                        const uint32_t ss = rs::smem_u32(stages + stage * kStageBytes);
+                        const uint32_t sa = kResident ? rs::smem_u32(a_res + (ab * 4 + kb) * PIECE_BYTES) : ss;
+                        const uint32_t sb = kResident ? ss : ss + PIECE_BYTES;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t da = rs::umma_desc_noswz(sa + k * 2 * CHUNK_BYTES, CHUNK_BYTES, 128);
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtPar
                         rs::tc_commit(&empty_bar[stage]);
                         if (kb == p.k_blocks - 1) {
                             rs::tc_commit(&acc_full[acc]);
-                            if (kResident && n == p.n_tiles - 1) rs::tc_commit(a_empty);
+                            if (kResident && n == p.n_tiles - 1) rs::tc_commit(&a_empty[ab]);
                         }
                     }
                     __syncwarp();
@@ -120,35 +131,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_nt_kernel(const NtPar
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (kResident && ++ab == 2) { ab = 0; a_phase ^= 1; }
         }
     } else {
         const int q = warp & 3, row = q * 32 + lane;
+        const int chalf = (warp - 2) >> 2;              // which 64 of the 128 tile columns this warp converts
         int acc = 0; uint32_t acc_phase = 0;
         for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
             uint8_t* cblk = p.C + (long long)m * p.c_block_bytes + row * 16;
             for (int n = 0; n < p.n_tiles; ++n) {
                 rs::mbar_wait(&acc_full[acc], acc_phase);
                 rs::tc_fence_after();
-                const uint32_t taddr = tmem_base + acc * 128 + (static_cast<uint32_t>(q * 32) << 16);
+                const uint32_t taddr = tmem_base + acc * 128 + chalf * 64 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t r[32];
                     rs::tmem_ld_32x32b_x32(taddr + c0, r);
                     rs::tmem_ld_wait();
+                    const float* bs = bias_s + n * 128 + chalf * 64 + c0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint32_t pk[4];
+                        const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            float v0 = __uint_as_float(r[8 * j + 2 * e]), v1 = __uint_as_float(r[8 * j + 2 * e + 1]);
-                            if (p.bias) {
-                                v0 += __ldg(&p.bias[n * 128 + c0 + 8 * j + 2 * e]);
-                                v1 += __ldg(&p.bias[n * 128 + c0 + 8 * j + 2 * e + 1]);
-                            }
+                            const float v0 = __uint_as_float(r[8 * j + 2 * e]) + bb[2 * e];
+                            const float v1 = __uint_as_float(r[8 * j + 2 * e + 1]) + bb[2 * e + 1];
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
                             pk[e] = *reinterpret_cast<uint32_t*>(&h2);
                         }
-                        const int chunk = p.c_chunk0 + n * 16 + c0 / 8 + j;
+                        const int chunk = p.c_chunk0 + n * 16 + chalf * 8 + c0 / 8 + j;
                         *reinterpret_cast<uint4*>(cblk + (long long)chunk * CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
@@ -424,15 +438,17 @@ extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk
     p.W = static_cast<const uint8_t*>(W);
     p.C = static_cast<uint8_t*>(C); p.c_block_bytes = c_cols * 256; p.c_chunk0 = c_chunk0;
     p.bias = bias; p.n_blocks = (int)n_blocks; p.n_tiles = n_tiles; p.k_blocks = k_blocks;
-    const int smem = 4 * PIECE_BYTES + NT_STAGES * 2 * PIECE_BYTES + 256;
+    RS_REQUIRE(n_tiles * 128 <= NT_MAX_N, "rs_blk_gemm_nt: at most %d output columns", NT_MAX_N);
     const int grid = (int)(n_blocks < num_sms() ? n_blocks : num_sms());
     if (k_blocks <= 4) {
+        const int smem = 2 * 4 * PIECE_BYTES + 5 * PIECE_BYTES + NT_MAX_N * 4 + 256;
         RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        blk_gemm_nt_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
+        blk_gemm_nt_kernel<true><<<grid, NT_THREADS, smem, stream>>>(p);
         rs::count_launch();
     } else {
+        const int smem = 6 * 2 * PIECE_BYTES + NT_MAX_N * 4 + 256;
         RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        blk_gemm_nt_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+        blk_gemm_nt_kernel<false><<<grid, NT_THREADS, smem, stream>>>(p);
         rs::count_launch();
     }
     RS_CUDA_OK(cudaGetLastError());

@@ -270,9 +270,10 @@ class DecoderFn(torch.autograd.Function):
         f1 = torch.empty(B, D1, device=dev)
         f2 = torch.empty(B, D2, device=dev)
         raw = torch.empty(B, NH, device=dev)
-        linear_nt(latent, W1.contiguous(), b1, f1, RELU)
-        linear_nt(f1, W2.contiguous(), b2, f2, RELU)
-        linear_nt(f2, Wh, bh, raw)
+        with ktime("decoder_fwd(sgemm x3)", 2.0 * B * (latent.shape[1] * D1 + D1 * D2 + D2 * NH)):
+            linear_nt(latent, W1.contiguous(), b1, f1, RELU)
+            linear_nt(f1, W2.contiguous(), b2, f2, RELU)
+            linear_nt(f2, Wh, bh, raw)
         cls = torch.empty(B, N, C, device=dev)
         pos = torch.empty(B, N, 2, device=dev)
         size = torch.empty(B, N, 2, device=dev)
@@ -292,6 +293,8 @@ class DecoderFn(torch.autograd.Function):
         st = torch.cuda.current_stream(dev).cuda_stream
         c = lambda t: t.contiguous() if t is not None else None  # noqa: E731
         d_cls, d_pos, d_size, d_orient, d_valid = c(d_cls), c(d_pos), c(d_size), c(d_orient), c(d_valid)
+        kt = ktime("decoder_bwd(sgemm x6)", 4.0 * B * (latent.shape[1] * W1.shape[0] + W1.shape[0] * W2.shape[0] + W2.shape[0] * Wh.shape[0]))
+        kt.__enter__()
         d_raw = torch.empty_like(raw)
         _lib.call("rs_heads_merge_bwd_f32", _p(raw), B, N, C, _p(d_cls), _p(d_pos), _p(d_size), _p(d_orient),
                   _p(d_valid), _p(d_raw), st)
@@ -315,6 +318,7 @@ class DecoderFn(torch.autograd.Function):
         colsum(df1, db1)
         dlat = torch.empty_like(latent)
         matmul_nn(df1, W1.contiguous(), dlat)
+        kt.__exit__(None, None, None)
         head_grads = []
         r0 = 0
         for rows in ctx.head_rows:
