@@ -133,6 +133,25 @@ class RoomSLAM(nn.Module):
         latent = torch.cat([h_n[-2], h_n[-1]], dim=-1)          # decision D5 (README.md:115)
         return self.decoder(latent)
 
+    @torch.no_grad()
+    def predict(self, x: torch.Tensor, batch_size: int = 16384) -> Dict[str, torch.Tensor]:
+        """Batched inference (BASELINE config 5: hundreds of thousands of traces): forward in chunks of `batch_size`
+        traces so that the per-timestep activations of one chunk fit in HBM; x may live on the host (each chunk is
+        copied to the model's device) and the predictions come back on x's device."""
+        was_training = self.training
+        self.eval()
+        dev = next(self.parameters()).device
+        outs = []
+        try:
+            for s in range(0, x.shape[0], batch_size):
+                xb = x[s:s + batch_size].to(dev, non_blocking=True)
+                outs.append({k: v.to(x.device) for k, v in self.forward(xb).items()})
+        finally:
+            self.train(was_training)
+        if not outs:
+            return self.forward(x.to(dev))
+        return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
     def compute_loss(self, pred: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         losses = F_.MultiTaskLossFn.apply(pred["class_logits"], pred["positions"], pred["sizes"], pred["orientations"],
                                           pred["validity_logits"], target["classes"], target["positions"],
