@@ -132,11 +132,13 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
                  const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols, const int* b_shift,
                  float* const* C, const int64_t* ldc, float* const* bias, int tiles, int T, void* stream);
 /* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
-/* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 3) fp32 + wx_packed [2][3H][4] = (w_ih row, bias);
- * deeper layers: P tile-major (6H columns, bias folded in).  Whh [2][16][384][8] bf16, b_hn [2][H], out tile-major
- * (2H columns, zero pad rows), gates [tiles][T][2][64][128][8] bf16 (NULL for inference), h_n [2][B][H] fp32. */
-int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, const void* P, int64_t p_cols, const void* Whh,
-                    const float* b_hn, void* out, void* gates, float* h_n, int B, int T, void* stream);
+/* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 2) fp32, its projection rides on the tensor core:
+ * Whh is then [2][18][384][8] bf16 with chunk 16 = per gate row (w_hi, w_hi, w_lo) per input and (b_hi, b_lo), chunk
+ * 17 = 0.  Deeper layers: P tile-major (6H columns, bias folded in) and Whh [2][16][384][8].  The r and z rows of all
+ * weights / biases carry the factor 1/2 of sigma(a) = tanh(a/2)/2 + 1/2.  b_hn [2][H], out tile-major (2H columns,
+ * zero pad rows), gates [tiles][T][2][64][128][8] fp16 (NULL for inference), h_n [2][B][H] fp32. */
+int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
+                    void* gates, float* h_n, int B, int T, void* stream);
 /* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
  * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,

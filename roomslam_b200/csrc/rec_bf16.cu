@@ -24,17 +24,17 @@ namespace {
 constexpr int H = 128;
 constexpr int CHUNK = 2048;                 // bytes of one 16-byte chunk column over 128 rows
 constexpr int W_BYTES = 3 * H * H * 2;      // 96 KB
-constexpr int A_FWD_BYTES = H * 128 * 2;    // 32 KB  (h tile)
+constexpr int A_FWD_BYTES = (H + 16) * 128 * 2;   // 36 KB  (h tile + one K=16 step for the layer-0 input columns)
+constexpr int WX_BYTES = 2 * 384 * 16;       // the two extra 16-byte chunk columns of the layer-0 weight image
 constexpr int A_BWD_BYTES = 3 * H * 128 * 2;  // 96 KB (dGh tile)
 constexpr int H32_BYTES = H * 128 * 4;      // 64 KB  (fp32 hidden state, forward)
 constexpr int NUM_THREADS = 320;            // warp 0: MMA issuer, warp 1: spare, warps 2..9: epilogue
 constexpr int EPI_THREADS = 256;
 
 struct FwdParams {
-    const float* x; int I;                  // layer 0: raw input (B, T, I <= 4), fused projection
-    const float4* wx;                       // [2][3H] packed (w0, w1, w2|0, bias) per gate row (bias = b_ih (+ b_hh for r, z))
+    const float* x; int I;                  // layer 0: raw input (B, T, I <= 4); its projection rides on the MMA (see below)
     const uint8_t* P; long long p_block_bytes;   // deeper layers: tile-major projection, C = 6H, bias folded in
-    const uint8_t* Whh;                     // [2][16][384][8] bf16 (B operand image)
+    const uint8_t* Whh;                     // [2][16 or 18][384][8] bf16 (B operand image; 18 chunks with the input rows)
     const float* b_hn;                      // [2][H]
     uint8_t* out; long long out_block_bytes;     // tile-major, C = 2H
     uint8_t* gates;                         // [tiles][T][2][64][128][8] fp16 (private to fwd/bwd) or NULL
@@ -82,13 +82,30 @@ __device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
 __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stg16(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// Layer-0 input columns of one trace row: per input c the triple (hi, lo, hi) with hi = bf16(x_c), lo = bf16(x_c - hi),
+// then (1, 1); at most 2 inputs fit the 8 columns of one 16-byte chunk.
+__device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
+    float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (xp) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i < I) {
+                const float v = __ldg(xp + i);
+                const float hi = __bfloat162float(__float2bfloat16_rn(v));
+                c[3 * i] = hi; c[3 * i + 1] = v - hi; c[3 * i + 2] = hi;
+            }
+        }
+    }
+    c[6] = 1.0f; c[7] = 1.0f;
+    return pack8(c);
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;                               // [16 chunks][384 rows][16 B]
-    uint8_t* a_s = smem + W_BYTES;                     // [16 chunks][128 rows][16 B]  h_{t-1}
+    uint8_t* a_s = smem + W_BYTES + WX_BYTES;          // [18 chunks][128 rows][16 B]  h_{t-1} | input columns
     uint8_t* h32_s = a_s + A_FWD_BYTES;                // [32 chunks of 4 floats][128 rows][16 B]  fp32 master copy of h
-    float4* wx_s = reinterpret_cast<float4*>(h32_s + H32_BYTES);   // [3H] (layer 0)
-    float* bhn_s = reinterpret_cast<float*>(wx_s + 3 * H);        // [H]
+    float* bhn_s = reinterpret_cast<float*>(h32_s + H32_BYTES);   // [H]
     uint64_t* bars = reinterpret_cast<uint64_t*>(bhn_s + H);
     uint64_t* w_full = bars;
     uint64_t* h_ready = bars + 1;       // epilogue -> MMA (8 arrivals, one per epilogue warp)
@@ -106,11 +123,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
         rs::fence_mbar_init();
     }
     if (warp == 0) rs::tmem_alloc<512>(tmem_slot);
-    for (int i = threadIdx.x; i < 3 * H; i += NUM_THREADS)
-        wx_s[i] = p.x ? p.wx[dir * 3 * H + i] : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = threadIdx.x; i < H; i += NUM_THREADS) bhn_s[i] = p.b_hn[dir * H + i];
     for (int i = threadIdx.x; i < (A_FWD_BYTES + H32_BYTES) / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
-    rs::fence_proxy_async();            // the zeroed h_0 must be visible to the tensor core (async proxy)
+    __syncthreads();
+    const bool fused_x = (p.x != nullptr);
+    if (fused_x && threadIdx.x < 128) {     // input columns of the first step
+        const long long b = (long long)tile * 128 + threadIdx.x;
+        *reinterpret_cast<uint4*>(a_s + 16 * CHUNK + threadIdx.x * 16) =
+            pack_x(b < p.B ? p.x + (b * T + (dir ? T - 1 : 0)) * p.I : nullptr, p.I);
+    }
+    rs::fence_proxy_async();            // h_0 = 0 and the input columns must be visible to the tensor core (async proxy)
     rs::tc_fence_before();
     __syncthreads();
     rs::tc_fence_after();
@@ -118,17 +140,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
 
     if (warp == 0) {
         // ===================== W loader + MMA issuer =====================
+        const uint32_t w_bytes = fused_x ? (W_BYTES + WX_BYTES) : W_BYTES;
         if (lane == 0) {
-            rs::mbar_expect_tx(w_full, W_BYTES);
+            rs::mbar_expect_tx(w_full, w_bytes);
             for (int i = 0; i < 6; ++i)
-                rs::bulk_load(w_s + i * (W_BYTES / 6), p.Whh + (long long)dir * W_BYTES + i * (W_BYTES / 6), W_BYTES / 6, w_full);
+                rs::bulk_load(w_s + i * (w_bytes / 6), p.Whh + (long long)dir * w_bytes + i * (w_bytes / 6), w_bytes / 6, w_full);
         }
         rs::mbar_wait(w_full, 0);
         constexpr uint32_t idesc256 = rs::umma_idesc_bf16(128, 256, 0, 0);
         constexpr uint32_t idesc128 = rs::umma_idesc_bf16(128, 128, 0, 0);
         const uint32_t a_addr = rs::smem_u32(a_s), w_addr = rs::smem_u32(w_s);
         for (int step = 0; step < T; ++step) {
-            if (step > 0) {                       // h_0 = 0 is already in place for step 0
+            if (step > 0) {                       // h_0 = 0 (and the first input columns) are already in place for step 0
                 rs::mbar_wait(h_ready, (step - 1) & 1);
                 rs::tc_fence_after();
             }
@@ -139,7 +162,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                     const uint64_t db0 = rs::umma_desc_noswz(w_addr + k * 2 * (384 * 16), 384 * 16, 128);
                     const uint64_t db1 = rs::umma_desc_noswz(w_addr + k * 2 * (384 * 16) + 256 * 16, 384 * 16, 128);
                     rs::tc_mma_bf16(tmem_base, da, db0, idesc256, k != 0);          // r | z  -> columns [0, 256)
-                    rs::tc_mma_bf16(tmem_base + 256, da, db1, idesc128, k != 0);    // n      -> columns [256, 384)
+                    rs::tc_mma_bf16(tmem_base + 256, da, db1, idesc128, k != 0);    // W_hn h -> columns [256, 384)
+                }
+                if (fused_x) {
+                    // layer 0: one more K=16 step whose A columns are (x_hi, x_lo, x_hi) per input and (1, 1), against
+                    // (w_hi, w_hi, w_lo) and (b_hi, b_lo): W_ih x + b accurate to ~2^-16 although the operands are bf16.
+                    // r and z simply accumulate it; the n gate keeps it apart (r multiplies only the hidden part).
+                    const uint64_t da = rs::umma_desc_noswz(a_addr + 16 * CHUNK, CHUNK, 128);
+                    const uint64_t db0 = rs::umma_desc_noswz(w_addr + 16 * (384 * 16), 384 * 16, 128);
+                    const uint64_t db1 = rs::umma_desc_noswz(w_addr + 16 * (384 * 16) + 256 * 16, 384 * 16, 128);
+                    rs::tc_mma_bf16(tmem_base, da, db0, idesc256, 1u);
+                    rs::tc_mma_bf16(tmem_base + 384, da, db1, idesc128, 0u);        // W_in x + b_in -> columns [384, 512)
                 }
                 rs::tc_commit(acc_full);
             }
@@ -176,12 +209,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
             const uint8_t* pblk = p.P ? p.P + blk * p.p_block_bytes + (long long)(dir * 48) * CHUNK + row * 16 : nullptr;
             uint8_t* oblk = p.out + blk * p.out_block_bytes + (long long)(dir * 16) * CHUNK + row * 16;
             uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK) + row * 16 : nullptr;
-            float xin[4] = {0.f, 0.f, 0.f, 0.f};
-            if (xrow && live) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < p.I) xin[c] = __ldg(xrow + (long long)t * p.I + c);
-            }
+            // layer 0: the input columns of the NEXT step (one thread per row writes them before handing h_t over)
+            uint4 xnext = make_uint4(0, 0, 0, 0);
+            const bool write_x = fused_x && half == 0 && step + 1 < T;
+            if (write_x) xnext = pack_x(live ? xrow + (long long)(dir ? t - 1 : t + 1) * p.I : nullptr, p.I);
             // input-side pre-activations: 8 units (one 16-byte chunk per gate) per group, fetched one group ahead;
             // the first group of a step is requested before waiting for the tensor core
             uint4 pv[3];
@@ -192,10 +223,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
             if (pblk) load_p(0);
             rs::mbar_wait(acc_full, step & 1);
             rs::tc_fence_after();
-            uint32_t ar[8], az[8], an[8];
+            uint32_t ar[8], az[8], an[8], ax[8];
             rs::tmem_ld_32x32b_x8(taddr + half * 64, ar);
             rs::tmem_ld_32x32b_x8(taddr + 128 + half * 64, az);
             rs::tmem_ld_32x32b_x8(taddr + 256 + half * 64, an);
+            if (fused_x) rs::tmem_ld_32x32b_x8(taddr + 384 + half * 64, ax);
 #pragma unroll
             for (int grp = 0; grp < 8; ++grp) {
                 const int u0 = half * 64 + grp * 8;
@@ -203,14 +235,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                 if (pblk) {
                     unpack8(pv[0], pr); unpack8(pv[1], pz); unpack8(pv[2], pn);
                     if (grp < 7) load_p(grp + 1);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 wr = wx_s[u0 + j], wz = wx_s[H + u0 + j], wn = wx_s[2 * H + u0 + j];
-                        pr[j] = fmaf(wr.z, xin[2], fmaf(wr.y, xin[1], fmaf(wr.x, xin[0], wr.w)));
-                        pz[j] = fmaf(wz.z, xin[2], fmaf(wz.y, xin[1], fmaf(wz.x, xin[0], wz.w)));
-                        pn[j] = fmaf(wn.z, xin[2], fmaf(wn.y, xin[1], fmaf(wn.x, xin[0], wn.w)));
-                    }
                 }
                 {   // fp32 h_{t-1}: the blend must not re-round the state every step
                     const float4 v0 = *reinterpret_cast<const float4*>(h32_row + (u0 / 4) * CHUNK);
@@ -221,16 +245,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                 float gr_[8], gz_[8], gn_[8];        // this group's accumulator values; the registers are then reloaded
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { gr_[j] = __uint_as_float(ar[j]); gz_[j] = __uint_as_float(az[j]); gn_[j] = __uint_as_float(an[j]); }
+                if (!pblk) {                        // layer 0: the tensor core already added W_ih x + b to r and z
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { pr[j] = 0.0f; pz[j] = 0.0f; pn[j] = __uint_as_float(ax[j]); }
+                }
                 if (grp < 7) {                      // TMEM loads of the next group fly while this group is computed
                     rs::tmem_ld_32x32b_x8(taddr + u0 + 8, ar);
                     rs::tmem_ld_32x32b_x8(taddr + 128 + u0 + 8, az);
                     rs::tmem_ld_32x32b_x8(taddr + 256 + u0 + 8, an);
+                    if (fused_x) rs::tmem_ld_32x32b_x8(taddr + 384 + u0 + 8, ax);
                 }
                 float hv[8], rv[8], zv[8], nv[8], hnv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float r = fmaf(0.5f, tanh_fast(0.5f * (gr_[j] + pr[j])), 0.5f);
-                    const float z = fmaf(0.5f, tanh_fast(0.5f * (gz_[j] + pz[j])), 0.5f);
+                    // the host folds the 1/2 of sigma(a) = 1/2 tanh(a/2) + 1/2 into the r and z rows of W_hh, W_ih and the biases
+                    const float r = fmaf(0.5f, tanh_fast(gr_[j] + pr[j]), 0.5f);
+                    const float z = fmaf(0.5f, tanh_fast(gz_[j] + pz[j]), 0.5f);
                     const float hn = gn_[j] + bhn_s[u0 + j];
                     const float n = tanh_fast(fmaf(r, hn, pn[j]));
                     hv[j] = fmaf(z, ho[j] - n, n);
@@ -253,6 +283,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                     *reinterpret_cast<float4*>(hn_out + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
                 }
             }
+            if (write_x) *reinterpret_cast<uint4*>(a_row + 16 * CHUNK) = xnext;
             rs::fence_proxy_async();        // h_t written with ordinary stores -> visible to tcgen05.mma
             rs::tc_fence_before();          // our TMEM reads are done before the next MMA overwrites the accumulator
             __syncwarp();
@@ -471,12 +502,12 @@ int pf_dist_env(const char* name, int dflt) {
 
 }  // namespace
 
-extern "C" int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, const void* P, int64_t p_cols, const void* Whh,
+extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh,
                                const float* b_hn, void* out, void* gates, float* h_n, int B, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     RS_REQUIRE((x != nullptr) != (P != nullptr), "rs_rec_fwd_bf16: exactly one of x (layer 0) and P (deeper layers) must be given");
-    RS_REQUIRE(!x || (I >= 1 && I <= 3 && wx_packed), "rs_rec_fwd_bf16: fused input projection needs 1 <= I <= 3 and packed weights");
+    RS_REQUIRE(!x || (I >= 1 && I <= 2), "rs_rec_fwd_bf16: the MMA-fused input projection takes 1 or 2 input columns");
     RS_REQUIRE(!P || p_cols == 6 * H, "rs_rec_fwd_bf16: P must have 6H = %d columns", 6 * H);
     RS_REQUIRE(Whh && b_hn && out && h_n && B >= 0 && T >= 0, "rs_rec_fwd_bf16: bad arguments");
     if (B == 0) return 0;
@@ -485,13 +516,13 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const float* wx_packed, co
         return 0;
     }
     FwdParams p = {};
-    p.x = x; p.I = I; p.wx = reinterpret_cast<const float4*>(wx_packed);
+    p.x = x; p.I = I;
     p.P = static_cast<const uint8_t*>(P); p.p_block_bytes = 6LL * H * 256;
     p.Whh = static_cast<const uint8_t*>(Whh); p.b_hn = b_hn;
     p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
     p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.B = B; p.T = T;
     p.pf_dist = pf_dist_env("RS_PF_DIST_FWD", 1);
-    const int smem = W_BYTES + A_FWD_BYTES + H32_BYTES + 3 * H * 16 + H * 4 + 64;
+    const int smem = W_BYTES + WX_BYTES + A_FWD_BYTES + H32_BYTES + H * 4 + 64;
     RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     rec_fwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
     rs::count_launch();

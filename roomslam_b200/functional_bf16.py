@@ -87,39 +87,53 @@ class GRULayerBF16Fn(torch.autograd.Function):
         with torch.no_grad():
             w_ih_cat = torch.cat([w_ih, w_ih_r], 0).float()                       # [6H, Il]
             w_hh_cat = torch.stack([w_hh, w_hh_r], 0).float()                     # [2, 3H, H]
-            whh_img = w_hh_cat.to(torch.bfloat16).view(2, 3 * H, H // 8, 8).permute(0, 2, 1, 3).contiguous()
+            # sigma(a) = 1/2 tanh(a/2) + 1/2: the kernel evaluates tanh(acc + p) directly, so the r and z rows of W_hh,
+            # W_ih and the biases carry the factor 1/2 (an exact power-of-two scaling, no extra rounding)
+            half_rz = torch.ones(3 * H, device=dev)
+            half_rz[:2 * H] = 0.5
+            whh_img = (w_hh_cat * half_rz[None, :, None]).to(torch.bfloat16).view(2, 3 * H, H // 8, 8) \
+                .permute(0, 2, 1, 3).contiguous()
             b_hn = torch.stack([b_hh[2 * H:], b_hh_r[2 * H:]], 0).float().contiguous()
             bias_x = torch.stack([b_ih, b_ih_r], 0).float().clone()               # [2, 3H]
             bias_x[0, :2 * H] += b_hh[:2 * H]
             bias_x[1, :2 * H] += b_hh_r[:2 * H]
+            bias_x *= half_rz[None, :]
+            w_ih_fwd = (w_ih_cat.view(2, 3 * H, Il) * half_rz[None, :, None]).reshape(6 * H, Il)   # forward-only copy
             out = L.empty_tm(B, T, 2 * H, dev)
             h_n = torch.empty(2, B, H, device=dev)
             gates = torch.empty(tiles, T, 2, 64, L.TILE, 8, device=dev, dtype=torch.bfloat16) if need_grad else None
             rec_flops = 2.0 * B * T * 2 * 3 * H * H
             X = None
             if not padded_in:
-                if Il > 3:
-                    raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 3")
+                if Il > 2:
+                    raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 2")
                 x = xin.contiguous().float()
-                wx = torch.zeros(2, 3 * H, 4, device=dev)
-                wx[:, :, :Il] = w_ih_cat.view(2, 3 * H, Il)
-                wx[:, :, 3] = bias_x
+                # input rows of the weight image: (w_hi, w_hi, w_lo) per input and (b_hi, b_lo); see csrc/rec_bf16.cu
+                wv = w_ih_fwd.view(2, 3 * H, Il)
+                w_hi = wv.to(torch.bfloat16).float()
+                b_hi = bias_x.to(torch.bfloat16).float()
+                xcols = torch.zeros(2, 3 * H, 16, device=dev)
+                for c in range(Il):
+                    xcols[:, :, 3 * c] = w_hi[:, :, c]
+                    xcols[:, :, 3 * c + 1] = w_hi[:, :, c]
+                    xcols[:, :, 3 * c + 2] = wv[:, :, c] - w_hi[:, :, c]
+                xcols[:, :, 6] = b_hi
+                xcols[:, :, 7] = bias_x - b_hi
+                whh_img = torch.cat([whh_img, xcols.to(torch.bfloat16).view(2, 3 * H, 2, 8).permute(0, 2, 1, 3)], 1).contiguous()
                 with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
-                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, _p(wx), 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n),
-                              B, T, st)
+                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), B, T, st)
                 saved_in = x
             else:
                 X = xin
                 if mask is not None:
                     X = (xin * L.to_tile_major(mask)).contiguous()
                 P = torch.empty(tiles, T + 2, 6 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
-                wt = L.tile_weight_nt(w_ih_cat)                                    # [6][Il/64][8][128][8]
+                wt = L.tile_weight_nt(w_ih_fwd)                                    # [6][Il/64][8][128][8]
                 with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
                     _nt(X, Il, [8 * k for k in range(Il // 64)], wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
                 with ktime("rec_fwd_bf16_kernel", rec_flops):
-                    _lib.call("rs_rec_fwd_bf16", 0, 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n),
-                              B, T, st)
+                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), B, T, st)
                 del P
                 saved_in = X
         ctx.meta = (padded_in, B, T, Il)
