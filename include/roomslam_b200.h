@@ -125,12 +125,16 @@ int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blo
 int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles, const void* B,
                        int64_t b_cols, int b_chunk0, int n_cols, int b_shift, int b_broadcast, float* C, int64_t ldc,
                        int tiles, int T, void* stream);
-/* Fused weight-gradient pass of one layer: every role r < n_roles accumulates C[r][128, n_cols[r]] += sum over blocks
- * dG_blk[:, a_mchunk[r]*8 .. +128]^T . B[r]_blk'[:, b_chunk0[r]*8 .. + n_cols[r]] (time shift b_shift[r]) and, when
- * bias[r] != NULL, bias[r][128] += column sums of the same dG columns.  All arrays are HOST arrays of length n_roles. */
+/* Fused weight-gradient pass of one layer: every role r < n_roles (<= 18) accumulates C[r][128, n_cols[r]] += sum over
+ * blocks dG_blk[:, a_mchunk[r]*8 .. +128]^T . B[r]_blk'[:, b_chunk0[r]*8 .. + n_cols[r]] (time shift b_shift[r]; n_cols
+ * may be 0), when bias[r] != NULL bias[r][128] += column sums of the same dG columns, and when B2[r] != NULL
+ * C2[r][128, 16] += the same dG columns ^T . B2[r]_blk (a 16-column tile-major tensor, e.g. the layer-0 input).
+ * All arrays are HOST arrays of length n_roles.  Roles should do equal work per block (they share operands through
+ * L2 only while they advance in lockstep). */
 int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_roles, const int* a_mchunk,
                  const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols, const int* b_shift,
-                 float* const* C, const int64_t* ldc, float* const* bias, int tiles, int T, void* stream);
+                 float* const* C, const int64_t* ldc, float* const* bias, const void* const* B2, float* const* C2,
+                 int tiles, int T, void* stream);
 /* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
 /* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 2) fp32, its projection rides on the tensor core:
  * Whh is then [2][18][384][8] bf16 with chunk 16 = per gate row (w_hi, w_hi, w_lo) per input and (b_hi, b_lo), chunk

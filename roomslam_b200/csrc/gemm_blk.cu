@@ -285,12 +285,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_tn_kernel(const TnPar
 // Work item = (split of the block range, role); the roles of one split sit on neighbouring CTAs and walk the same
 // blocks at the same time, so a dG piece needed by two roles (and the B blocks shared by several) come from HBM once
 // and from L2 afterwards: dG is streamed from DRAM exactly once per layer instead of once per consumer.
-constexpr int WG_MAX_ROLES = 12;
+constexpr int WG_MAX_ROLES = 18;
 struct WgRole {
     int a_mchunk;                       // first 16-byte chunk of the dG columns of this role
     const uint8_t* B; long long b_block_bytes; int b_chunk0; int n_cols; int b_shift;
     float* C; long long ldc;            // C rows [0,128) x n_cols of this role
     float* bias;                        // 128 floats or NULL
+    const uint8_t* B2; long long b2_block_bytes;   // optional second B source: 16 columns (2 chunks), no time shift
+    float* C2; long long ldc2;          // 128 x 16
 };
 struct WgParams {
     const uint8_t* A; long long a_block_bytes;
@@ -301,7 +303,7 @@ struct WgParams {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int stage_bytes = 2 * PIECE_BYTES + p.max_b_bytes;
+    const int stage_bytes = 2 * PIECE_BYTES + p.max_b_bytes + 2 * CHUNK_BYTES;   // A | B | B2 (16 columns)
     uint8_t* stages = smem;
     uint8_t* ones_s = smem + 2 * stage_bytes;                    // 4 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(ones_s + 2 * CHUNK_BYTES);
@@ -343,15 +345,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
                     const long long blk = (long long)(i / p.T) * p.Tp + 1 + (i % p.T);
                     rs::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = stages + stage * stage_bytes;
-                    rs::mbar_expect_tx(&full_bar[stage], 2 * PIECE_BYTES + b_bytes);
+                    rs::mbar_expect_tx(&full_bar[stage], 2 * PIECE_BYTES + b_bytes + (R.B2 ? 2 * CHUNK_BYTES : 0));
                     rs::bulk_load(sa, p.A + blk * p.a_block_bytes + (long long)R.a_mchunk * CHUNK_BYTES, 2 * PIECE_BYTES, &full_bar[stage]);
-                    rs::bulk_load(sa + 2 * PIECE_BYTES, R.B + (blk + R.b_shift) * R.b_block_bytes + (long long)R.b_chunk0 * CHUNK_BYTES,
-                                  b_bytes, &full_bar[stage]);
+                    if (b_bytes)
+                        rs::bulk_load(sa + 2 * PIECE_BYTES, R.B + (blk + R.b_shift) * R.b_block_bytes + (long long)R.b_chunk0 * CHUNK_BYTES,
+                                      b_bytes, &full_bar[stage]);
+                    if (R.B2)
+                        rs::bulk_load(sa + 2 * PIECE_BYTES + p.max_b_bytes, R.B2 + blk * R.b2_block_bytes, 2 * CHUNK_BYTES, &full_bar[stage]);
                     if (++stage == 2) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1) {
-            const uint32_t idesc = rs::umma_idesc_bf16(128, R.n_cols, 1, 1);
+            const uint32_t idesc = rs::umma_idesc_bf16(128, R.n_cols ? R.n_cols : 16, 1, 1);
             const uint32_t idesc1 = rs::umma_idesc_bf16(128, 16, 1, 1);
             rs::mbar_wait(ones_full, 0);
             const uint32_t so = rs::smem_u32(ones_s);
@@ -364,11 +369,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {       // 128 traces = 8 K-steps of 16
                         const uint64_t da = rs::umma_desc_noswz(sa + k * 256, 128, CHUNK_BYTES);
-                        const uint64_t db = rs::umma_desc_noswz(sb + k * 256, 128, CHUNK_BYTES);
-                        rs::tc_mma_bf16(tmem_base, da, db, idesc, (i != i0) || (k != 0));
+                        if (R.n_cols) {
+                            const uint64_t db = rs::umma_desc_noswz(sb + k * 256, 128, CHUNK_BYTES);
+                            rs::tc_mma_bf16(tmem_base, da, db, idesc, (i != i0) || (k != 0));
+                        }
                         if (R.bias) {
                             const uint64_t d1 = rs::umma_desc_noswz(so + k * 256, 128, CHUNK_BYTES);
                             rs::tc_mma_bf16(tmem_base + 256, da, d1, idesc1, (i != i0) || (k != 0));
+                        }
+                        if (R.B2) {
+                            const uint64_t d2 = rs::umma_desc_noswz(sb + p.max_b_bytes + k * 256, 128, CHUNK_BYTES);
+                            rs::tc_mma_bf16(tmem_base + 272, da, d2, idesc1, (i != i0) || (k != 0));
                         }
                     }
                     rs::tc_commit(&empty_bar[stage]);
@@ -395,6 +406,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
                 rs::tmem_ld_32x32b_x8(taddr + 256, r);
                 rs::tmem_ld_wait();
                 atomicAdd(R.bias + row, __uint_as_float(r[0]));
+            }
+            if (R.B2) {
+                uint32_t r[16];
+                rs::tmem_ld_32x32b_x16(taddr + 272, r);
+                rs::tmem_ld_wait();
+                float* c2 = R.C2 + (long long)row * R.ldc2;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(c2 + j, __uint_as_float(r[j]));
             }
             rs::tc_fence_before();
         }
@@ -495,11 +514,11 @@ extern "C" int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mc
 // C[r] (fp32, 128 x n_cols[r], leading dimension ldc[r]), bias[r] (128 floats or NULL).  Outputs are ACCUMULATED into.
 extern "C" int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_roles, const int* a_mchunk,
                             const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols,
-                            const int* b_shift, float* const* C, const int64_t* ldc, float* const* bias, int tiles, int T,
-                            void* stream_) {
+                            const int* b_shift, float* const* C, const int64_t* ldc, float* const* bias,
+                            const void* const* B2, float* const* C2, int tiles, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
-    RS_REQUIRE(dG && ones_block && a_mchunk && B && b_cols && b_chunk0 && n_cols && b_shift && C && ldc && bias,
+    RS_REQUIRE(dG && ones_block && a_mchunk && B && b_cols && b_chunk0 && n_cols && b_shift && C && ldc && bias && B2 && C2,
                "rs_blk_wgrad: null pointer");
     RS_REQUIRE(n_roles >= 1 && n_roles <= WG_MAX_ROLES, "rs_blk_wgrad: 1 <= n_roles <= %d", WG_MAX_ROLES);
     const long long total = (long long)tiles * T;
@@ -512,12 +531,15 @@ extern "C" int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_blo
     int max_n = 16;
     for (int r = 0; r < n_roles; ++r) {
         RS_REQUIRE(a_mchunk[r] >= 0 && (a_mchunk[r] + 16) * 8 <= a_cols, "rs_blk_wgrad: role %d columns outside dG", r);
-        RS_REQUIRE(n_cols[r] >= 16 && n_cols[r] <= 256 && n_cols[r] % 16 == 0, "rs_blk_wgrad: role %d n_cols", r);
-        RS_REQUIRE(b_chunk0[r] * 8 + n_cols[r] <= b_cols[r] && B[r] && C[r], "rs_blk_wgrad: role %d B/C", r);
+        RS_REQUIRE(n_cols[r] >= 0 && n_cols[r] <= 256 && n_cols[r] % 16 == 0, "rs_blk_wgrad: role %d n_cols", r);
+        RS_REQUIRE(n_cols[r] == 0 || (b_chunk0[r] * 8 + n_cols[r] <= b_cols[r] && B[r] && C[r]), "rs_blk_wgrad: role %d B/C", r);
+        RS_REQUIRE(n_cols[r] > 0 || B2[r] || bias[r], "rs_blk_wgrad: role %d has nothing to do", r);
+        RS_REQUIRE(!B2[r] || C2[r], "rs_blk_wgrad: role %d has B2 but no C2", r);
         RS_REQUIRE(b_shift[r] >= -1 && b_shift[r] <= 1, "rs_blk_wgrad: role %d shift", r);
         WgRole& R = p.role[r];
         R.a_mchunk = a_mchunk[r]; R.B = static_cast<const uint8_t*>(B[r]); R.b_block_bytes = b_cols[r] * 256;
         R.b_chunk0 = b_chunk0[r]; R.n_cols = n_cols[r]; R.b_shift = b_shift[r]; R.C = C[r]; R.ldc = ldc[r]; R.bias = bias[r];
+        R.B2 = static_cast<const uint8_t*>(B2[r]); R.b2_block_bytes = 16 * 256; R.C2 = C2[r]; R.ldc2 = 16;
         if (n_cols[r] > max_n) max_n = n_cols[r];
     }
     p.max_b_bytes = max_n * 256;
@@ -526,7 +548,7 @@ extern "C" int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_blo
     if (splits > total) splits = (int)total;
     p.blocks_per_split = (int)((total + splits - 1) / splits);
     p.splits = (int)((total + p.blocks_per_split - 1) / p.blocks_per_split);
-    const int smem = 2 * (2 * PIECE_BYTES + p.max_b_bytes) + 2 * CHUNK_BYTES + 256;
+    const int smem = 2 * (2 * PIECE_BYTES + p.max_b_bytes + 2 * CHUNK_BYTES) + 2 * CHUNK_BYTES + 256;
     RS_CUDA_OK(cudaFuncSetAttribute(blk_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int items = n_roles * p.splits;
     blk_wgrad_kernel<<<items < num_sms() ? items : num_sms(), NUM_THREADS, smem, stream>>>(p);

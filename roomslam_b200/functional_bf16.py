@@ -37,22 +37,26 @@ def _tn(A, a_cols, mchunks, rows, Bm, b_cols, b_chunk0, n_cols, shift, bcast, C,
 
 
 def _wgrad(dG, a_cols, ones, roles, tiles, T, st):
-    """roles: list of (a_mchunk, B tensor, b_cols, b_chunk0, n_cols, b_shift, C tensor view, ldc, bias view or None)."""
+    """roles: list of (a_mchunk, B tensor or None, b_cols, b_chunk0, n_cols, b_shift, C view or None, ldc, bias view or None,
+    B2 tensor or None, C2 view or None)."""
     n = len(roles)
     vp = ctypes.c_void_p * n
     i64 = ctypes.c_int64 * n
     a_m = L.int_array([r[0] for r in roles])
-    Bp = vp(*[r[1].data_ptr() for r in roles])
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    Bp = vp(*[ptr(r[1]) for r in roles])
     b_cols = i64(*[r[2] for r in roles])
     b_c0 = L.int_array([r[3] for r in roles])
     n_cols = L.int_array([r[4] for r in roles])
     shift = L.int_array([r[5] for r in roles])
-    Cp = vp(*[r[6].data_ptr() for r in roles])
+    Cp = vp(*[ptr(r[6]) for r in roles])
     ldc = i64(*[r[7] for r in roles])
-    bias = vp(*[(r[8].data_ptr() if r[8] is not None else None) for r in roles])
+    bias = vp(*[ptr(r[8]) for r in roles])
+    B2p = vp(*[ptr(r[9]) for r in roles])
+    C2p = vp(*[ptr(r[10]) for r in roles])
     adr = ctypes.addressof
     _lib.call("rs_blk_wgrad", _p(dG), a_cols, _p(ones), n, adr(a_m), adr(Bp), adr(b_cols), adr(b_c0), adr(n_cols), adr(shift),
-              adr(Cp), adr(ldc), adr(bias), tiles, T, st)
+              adr(Cp), adr(ldc), adr(bias), adr(B2p), adr(C2p), tiles, T, st)
 
 
 _ONES = {}
@@ -167,23 +171,36 @@ class GRULayerBF16Fn(torch.autograd.Function):
             #   hh roles (dir, g in r,z,hn): dG block ^T . h(t' -/+ 1) -> dW_hh rows, bias sum of hn
             dW_hh = torch.zeros(2, 3 * H, H, device=dev)
             sums = torch.zeros(2, 4, H, device=dev)              # per direction: r | z | n | hn column sums of dG
+            roles = []
             if not padded_in:
+                # layer 0: the input has 2 columns -> it rides along as the 16-column second B source of the hh roles
                 xa = torch.zeros(B, T, 16, device=dev)
                 xa[:, :, :Il] = saved_in
-                Xb, xb_cols, n_ih = L.to_tile_major(xa), 16, 16
+                xa_tm = L.to_tile_major(xa)
+                dW_ih_buf = torch.zeros(6 * H, 16, device=dev)
+                for d in (0, 1):
+                    sh = -1 if d == 0 else 1
+                    for g in (0, 1):                               # r, z: hidden-side block + input-side columns + bias sum
+                        roles.append((d * 64 + g * 16, out, 2 * H, d * 16, H, sh, dW_hh[d, g * H:], H, sums[d, g],
+                                      xa_tm, dW_ih_buf[(d * 3 + g) * H:]))
+                    roles.append((d * 64 + 48, out, 2 * H, d * 16, H, sh, dW_hh[d, 2 * H:], H, sums[d, 3], None, None))   # hn
+                    roles.append((d * 64 + 32, None, 0, 0, 0, 0, None, 0, sums[d, 2], xa_tm, dW_ih_buf[(d * 3 + 2) * H:]))  # n
+                flops = 2.0 * tiles * L.TILE * T * (6 * H * 16 + 6 * H * H + 8 * H * 16)
             else:
-                Xb, xb_cols, n_ih = saved_in, Il, Il
-            if n_ih > 256:
-                raise _lib.RoomSlamError("bf16 mode: layer input wider than 256 columns is not supported")
-            dW_ih_buf = torch.zeros(6 * H, n_ih, device=dev)
-            roles = []
-            for d in (0, 1):
-                for g in (0, 1, 2):                                # r, z, n against the layer input
-                    roles.append((d * 64 + g * 16, Xb, xb_cols, 0, n_ih, 0, dW_ih_buf[(d * 3 + g) * H:], n_ih, sums[d, g]))
-                for gi, g in enumerate((0, 1, 3)):                 # r, z, hn against the shifted hidden state
-                    roles.append((d * 64 + g * 16, out, 2 * H, d * 16, H, -1 if d == 0 else 1, dW_hh[d, gi * H:], H,
-                                  sums[d, 3] if g == 3 else None))
-            flops = 2.0 * tiles * L.TILE * T * (6 * H * n_ih + 6 * H * H + 8 * H * 16)
+                # deeper layers: 12 roles: ih (N = 2H) and hh (N = H) per gate block.  (18 equal-weight N = H roles were
+                # tried to keep the roles in lockstep for L2 sharing: slower, 6.1 ms vs 5.5 ms - more L2->SM traffic.)
+                if Il != 2 * H:
+                    raise _lib.RoomSlamError("bf16 mode: deeper layers take the 2H-column output of the layer below")
+                dW_ih_buf = torch.zeros(6 * H, Il, device=dev)
+                for d in (0, 1):
+                    sh = -1 if d == 0 else 1
+                    for g in (0, 1, 2):                            # r, z, n against the layer input
+                        roles.append((d * 64 + g * 16, saved_in, Il, 0, Il, 0, dW_ih_buf[(d * 3 + g) * H:], Il, sums[d, g],
+                                      None, None))
+                    for gi, g in enumerate((0, 1, 3)):             # r, z, hn against the shifted hidden state
+                        roles.append((d * 64 + g * 16, out, 2 * H, d * 16, H, sh, dW_hh[d, gi * H:], H,
+                                      sums[d, 3] if g == 3 else None, None, None))
+                flops = 2.0 * tiles * L.TILE * T * (6 * H * Il + 6 * H * H + 8 * H * 16)
             with ktime("blk_wgrad_kernel", flops):
                 _wgrad(dG, 8 * H, _ones_block(dev), roles, tiles, T, st)
             db_ih = sums[:, :3].reshape(2, 3 * H)
