@@ -51,6 +51,7 @@ int rs_heatmap_bin_host(const float* host_points, int64_t n_traces, int64_t seq_
  * use rows = T, row0 = 0; the library's padded activation layout uses rows = T + 2, row0 = 1 with zero pad rows. */
 #define RS_GEMM_ACCUMULATE 1
 #define RS_GEMM_RELU 2
+#define RS_GEMM_OUT_F32 4
 /* C[m,n] = act(sum_k A[m*a_sm + k*a_sk] * B[k*b_sk + n*b_sn] + bias[n]) (+ C).  fp32 CUDA-core GEMM. */
 int rs_sgemm(const float* A, int64_t a_sm, int64_t a_sk, const float* B, int64_t b_sk, int64_t b_sn, float* C,
              int64_t ldc, const float* bias, int M, int N, int K, int flags, void* stream);
@@ -81,6 +82,7 @@ int rs_heads_split_f32(const float* raw, int B, int N, int C, float* cls, float*
 int rs_heads_merge_bwd_f32(const float* raw, int B, int N, int C, const float* d_cls, const float* d_pos,
                            const float* d_size, const float* d_orient, const float* d_valid, float* d_raw, void* stream);
 int rs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+int rs_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, void* stream);   /* bf16 tensors */
 /* Multi-task loss (README.md:122-125): weights5 is a HOST array {class, position, size, orientation, validity}.
  * losses6 = {total, class, position, size, orientation, validity}; sums6 (double) and g_* keep what backward needs. */
 int rs_loss_fwd_f32(const float* cls, const float* pos, const float* size, const float* orient, const float* vlogit,
@@ -93,10 +95,11 @@ int rs_loss_bwd_f32(const double* sums6, const float* d_losses6, int B, int N, i
                     void* stream);
 
 /* ---- bf16 tensor-core GEMMs (tcgen05 + TMEM accumulators, TMA-fed): the time-parallel work of the bf16 mode ---- */
-/* C[M,N] (bf16, ldc) = A[M,K] (bf16, lda) . B[N,K]^T (bf16, ldb) + bias[N] (fp32, optional).  K % 64 == 0, N % 128 == 0,
- * leading dimensions in elements and multiples of 8.  Input projection P = X W_ih^T + b_ih and dX = dG W_ih. */
+/* C[M,N] (ldc) = act(A[M,K] (bf16, lda) . B[N,K]^T (bf16, ldb) + bias[N] (fp32, optional)).  K % 64 == 0, N % 128 == 0,
+ * leading dimensions in elements and multiples of 8.  flags: RS_GEMM_RELU, RS_GEMM_OUT_F32 (C is fp32 and written
+ * with direct row stores; default: bf16 through TMA stores).  TMA-fed tcgen05: the decoder MLP of the bf16 mode. */
 int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, const float* bias,
-                    int64_t M, int N, int K, void* stream);
+                    int64_t M, int N, int K, int flags, void* stream);
 /* C[M,N] (fp32, ldc) += A[:, a_col0:a_col0+M]^T . B[:, b_col0:b_col0+N], reduction over `rows` row pairs
  * (row r + a_row_shift of A with row r + b_row_shift of B; rows outside a matrix count as zero).  M, N % 128 == 0.
  * Weight gradients dW_ih = dGx^T X and dW_hh = dGh^T H_prev (one-row shift between the operands). */

@@ -66,6 +66,12 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __res
         dx[e] = y[e] > 0.0f ? dy[e] : 0.0f;
 }
 
+__global__ void relu_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ dx, long long n) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        dx[e] = __bfloat162float(y[e]) > 0.0f ? dy[e] : __float2bfloat16(0.0f);
+}
+
 __device__ __forceinline__ float sgn(float d) { return (d > 0.0f) - (d < 0.0f); }
 
 // sums: [0] n_valid, [1] ce, [2] |dpos|, [3] |dsize|, [4] |dorient|, [5] bce   (double accumulators)
@@ -201,6 +207,18 @@ extern "C" int rs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64
     RS_REQUIRE(dy && y && dx, "rs_relu_bwd_f32: null pointer");
     if (n == 0) return 0;
     relu_bwd_kernel<<<blocks_for(n), 256, 0, stream>>>(dy, y, dx, n);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(dy && y && dx, "rs_relu_bwd_bf16: null pointer");
+    if (n == 0) return 0;
+    relu_bwd_bf16_kernel<<<blocks_for(n), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+                                                            static_cast<__nv_bfloat16*>(dx), n);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -35,6 +35,8 @@ struct GemmParams {
     int a_row_shift, b_row_shift;   // TN: row offsets applied to the TMA coordinates of A and B
     int a_col0, b_col0;     // TN: column offsets inside the global matrices (select a column block)
     const float* bias;      // NT: optional
+    int flags;              // NT: RS_GEMM_RELU, RS_GEMM_OUT_F32
+    float* c_nt_f32; long long ldc_nt;   // NT with fp32 output: direct row stores
     float* c_f32;           // TN: output
     long long ldc;          // TN: leading dimension of C (floats)
 };
@@ -157,7 +159,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             rs::mbar_wait(&acc_full[acc], acc_phase);
             rs::tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-            if (!kTN) {
+            if (!kTN && (p.flags & RS_GEMM_OUT_F32)) {
+                // fp32 result: each thread writes its own row (small outputs only: decoder heads)
+                const long long gm = (long long)m_blk * BM + row;
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    rs::tmem_ld_32x32b_x32(taddr + c0, r);
+                    rs::tmem_ld_wait();
+                    if (gm < p.M) {
+                        float* crow = p.c_nt_f32 + gm * p.ldc_nt + n_blk * BN + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v;
+                            v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]); v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                            if (p.bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + c0 + j));
+                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                            }
+                            if (p.flags & RS_GEMM_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4*>(crow + j) = v;
+                        }
+                    }
+                }
+                rs::tc_fence_before();
+                if (lane == 0) rs::mbar_arrive(&acc_empty[acc]);
+            } else if (!kTN) {
                 // make sure the previous TMA store has finished reading the staging tile
                 if (warp == 2 && lane == 0) rs::tma_store_wait_read<0>();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -174,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             v0 += __ldg(&p.bias[n_blk * BN + c0 + 2 * j]);
                             v1 += __ldg(&p.bias[n_blk * BN + c0 + 2 * j + 1]);
                         }
+                        if (p.flags & RS_GEMM_RELU) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
                         packed[j] = *reinterpret_cast<uint32_t*>(&h2);
                     }
@@ -215,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (!kTN && warp == 2 && lane == 0) rs::tma_store_wait<0>();
+        if (!kTN && !(p.flags & RS_GEMM_OUT_F32) && warp == 2 && lane == 0) rs::tma_store_wait<0>();
     }
 
     rs::tc_fence_before();
@@ -239,25 +267,27 @@ int num_sms() {
 
 // C[M,N] (bf16, leading dimension ldc) = A[M,K] (lda) . B[N,K]^T (ldb) + bias.  K % 64 == 0, N % 128 == 0.
 extern "C" int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
-                               const float* bias, int64_t M, int N, int K, void* stream_) {
+                               const float* bias, int64_t M, int N, int K, int flags, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     RS_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0, "rs_gemm_bf16_nt: bad arguments");
     RS_REQUIRE(K % BK == 0 && N % BN == 0, "rs_gemm_bf16_nt: need K %% 64 == 0 and N %% 128 == 0 (got N=%d K=%d)", N, K);
     RS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "rs_gemm_bf16_nt: leading dimensions must be multiples of 8");
+    const bool out_f32 = flags & RS_GEMM_OUT_F32;
     RS_REQUIRE(M < (1ll << 31), "rs_gemm_bf16_nt: M too large");
     if (M == 0) return 0;
     CUtensorMap ta, tb, tc;
     if (rs::make_tmap_2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda * 2, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (rs::make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb * 2, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
-    if (rs::make_tmap_2d(&tc, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, M, ldc * 2, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+    if (out_f32) tc = ta;      // unused by the kernel in this mode
+    else if (rs::make_tmap_2d(&tc, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, M, ldc * 2, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     GemmParams p = {};
     p.M = (int)M; p.N = N; p.K = K;
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.n_tiles = N / BN;
     p.k_blocks = K / BK;
     p.splits = 1;
-    p.bias = bias;
+    p.bias = bias; p.flags = flags; p.c_nt_f32 = static_cast<float*>(C); p.ldc_nt = ldc;
     RS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     long long tiles = (long long)p.m_tiles * p.n_tiles;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());

@@ -49,11 +49,12 @@ class GRUParams(nn.Module):
 
 class Decoder(nn.Module):
     """Parameter container for the MLP decoder (README.md:117-120; decision D6).  nn.Linear is used only to hold
-    and initialise weights; the math runs in DecoderFn."""
+    and initialise weights; the math runs in DecoderFn (fp32 CUDA-core GEMM) or DecoderBF16Fn (TMA-fed tcgen05 GEMM)."""
 
-    def __init__(self, in_features: int, hidden: int, max_objects: int, num_classes: int):
+    def __init__(self, in_features: int, hidden: int, max_objects: int, num_classes: int, precision: str = "fp32"):
         super().__init__()
         self.max_objects, self.num_classes = max_objects, num_classes
+        self.precision = precision
         self.trunk = nn.Sequential(nn.Linear(in_features, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU())
         self.class_head = nn.Linear(hidden, max_objects * num_classes)
         self.pos_head = nn.Linear(hidden, max_objects * 2)
@@ -65,7 +66,13 @@ class Decoder(nn.Module):
         heads = []
         for h in (self.class_head, self.pos_head, self.size_head, self.orient_head, self.valid_head):
             heads += [h.weight, h.bias]
-        cls, pos, size, orient, valid = F_.DecoderFn.apply(
+        fn = F_.DecoderFn
+        # bf16 mode: tensor-core decoder from 256 traces up.  Below that the GEMMs are latency-bound anyway and a single
+        # bf16-induced ReLU flip moves the gradient of a 3-trace batch by several per cent (tools/bf16_err_probe.py).
+        if self.precision == "bf16" and latent.shape[0] >= 256 and latent.shape[1] % 64 == 0 \
+                and self.trunk[0].out_features % 128 == 0 and self.trunk[2].out_features % 128 == 0:
+            from .functional_bf16 import DecoderBF16Fn as fn
+        cls, pos, size, orient, valid = fn.apply(
             latent, self.max_objects, self.num_classes, self.trunk[0].weight, self.trunk[0].bias,
             self.trunk[2].weight, self.trunk[2].bias, *heads)
         return {"class_logits": cls, "positions": pos, "sizes": size, "orientations": orient, "validity_logits": valid}
@@ -83,7 +90,7 @@ class RoomSLAM(nn.Module):
         self.max_objects, self.num_classes, self.dropout = max_objects, num_classes, dropout
         self.precision = precision
         self.encoder = GRUParams(input_size, hidden_size, num_layers)
-        self.decoder = Decoder(2 * hidden_size, decoder_hidden, max_objects, num_classes)
+        self.decoder = Decoder(2 * hidden_size, decoder_hidden, max_objects, num_classes, precision)
 
     # -- dropout mask (decision D4: explicit Bernoulli mask so oracle and kernel see the same one) ----------
     def make_dropout_mask(self, batch: int, seq_len: int, generator: Optional[torch.Generator] = None,

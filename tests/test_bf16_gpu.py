@@ -29,7 +29,8 @@ def to_cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
-@pytest.mark.parametrize("B,T,L,use_mask", [(4, 12, 1, False), (130, 40, 2, False), (37, 25, 2, True), (256, 500, 2, False)])
+@pytest.mark.parametrize("B,T,L,use_mask", [(4, 12, 1, False), (130, 40, 2, False), (37, 25, 2, True), (256, 500, 2, False),
+                                            (1, 1, 2, False), (3, 2, 2, False), (129, 3, 1, False)])
 def test_bf16_matches_oracle(B, T, L, use_mask):
     torch.manual_seed(B + T)
     ref = RefRoomSLAM(num_layers=L, dropout=0.1 if use_mask else 0.0)

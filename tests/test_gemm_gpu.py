@@ -19,7 +19,7 @@ def test_gemm_bf16_nt_row_major(M, N, K, bias):
     A = torch.randn(M, K, device="cuda").bfloat16(); B = torch.randn(N, K, device="cuda").bfloat16()
     b = torch.randn(N, device="cuda") if bias else None
     C = torch.full((M, N), 7.0, device="cuda").bfloat16()
-    _lib.call("rs_gemm_bf16_nt", A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, b.data_ptr() if bias else 0, M, N, K, st())
+    _lib.call("rs_gemm_bf16_nt", A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, b.data_ptr() if bias else 0, M, N, K, 0, st())
     ref = A.float() @ B.float().t() + (b if bias else 0)
     assert float((C.float() - ref).abs().max() / ref.abs().max()) < 6e-3       # bf16 output rounding
 

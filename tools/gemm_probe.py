@@ -11,7 +11,7 @@ def nt(M, N, K, bias=True):
     A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
     b = torch.randn(N, device=dev) if bias else None
     C = torch.full((M, N), 7.0, device=dev).bfloat16()
-    _lib.call("rs_gemm_bf16_nt", A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, b.data_ptr() if bias else 0, M, N, K, st())
+    _lib.call("rs_gemm_bf16_nt", A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), N, b.data_ptr() if bias else 0, M, N, K, 0, st())
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t() + (b if bias else 0)
     err = (C.float() - ref).abs().max().item() / ref.abs().max().item()
