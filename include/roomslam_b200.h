@@ -146,6 +146,8 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
  * zero pad rows), gates [tiles][T][2][64][128][8] fp16 (NULL for inference), h_n [2][B][H] fp32. */
 int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
                     void* gates, float* h_n, int B, int T, void* stream);
+/* x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (zero padded): layer-0 input for rs_blk_wgrad. */
+int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 /* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
  * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,

@@ -492,6 +492,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
 // Tuning knobs: L2 bulk-prefetch distance in steps (0 = off).  Measured at B = 8192 (tools/step_probe.py): the forward
 // kernel is fastest one step ahead (6.8 ms vs 7.4 ms off); the backward kernel is fastest WITHOUT prefetch (7.3 ms vs
 // 9.7 ms at distance 3: it already runs at ~86 % of the HBM peak, extra prefetches only get evicted and re-read).
+// x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (the rest zero), pad rows and pad traces zero:
+// the B operand that carries the layer-0 input into the fused weight-gradient pass.
+__global__ void pack_x_tm_kernel(const float* __restrict__ x, int B, int T, int I, uint4* __restrict__ out, long long n_rows) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_rows; e += (long long)gridDim.x * blockDim.x) {
+        const int row = e & 127;                       // e = ((tile * (T+2) + t') * 128 + row)
+        const long long bt = e >> 7;
+        const int tp = bt % (T + 2);
+        const long long b = (bt / (T + 2)) * 128 + row;
+        float c[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = 0.0f;
+        if (b < B && tp >= 1 && tp <= T) {
+            const float* xp = x + (b * T + (tp - 1)) * I;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < I) c[i] = __ldg(xp + i);
+        }
+        const long long blk = bt * 256;                // 2 chunks x 128 rows of uint4 per block
+        out[blk + row] = pack8(c);
+        out[blk + 128 + row] = pack8(c + 8);
+    }
+}
+
 int pf_dist_env(const char* name, int dflt) {
     const char* e = getenv(name);
     int v = e ? atoi(e) : dflt;
@@ -547,6 +570,20 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
     const int smem = W_BYTES + A_BWD_BYTES + 64;
     RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     rec_bwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(x && out && B >= 0 && T >= 0 && I >= 1 && I <= 16, "rs_pack_x_tm: bad arguments");
+    const long long n_rows = (long long)((B + 127) / 128) * (T + 2) * 128;
+    if (n_rows == 0) return 0;
+    long long blocks = (n_rows + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_x_tm_kernel<<<(int)blocks, 256, 0, stream>>>(x, B, T, I, static_cast<uint4*>(out), n_rows);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -174,9 +174,8 @@ class GRULayerBF16Fn(torch.autograd.Function):
             roles = []
             if not padded_in:
                 # layer 0: the input has 2 columns -> it rides along as the 16-column second B source of the hh roles
-                xa = torch.zeros(B, T, 16, device=dev)
-                xa[:, :, :Il] = saved_in
-                xa_tm = L.to_tile_major(xa)
+                xa_tm = torch.empty(tiles, T + 2, 2, L.TILE, 8, device=dev, dtype=torch.bfloat16)
+                _lib.call("rs_pack_x_tm", _p(saved_in), B, T, Il, _p(xa_tm), st)
                 dW_ih_buf = torch.zeros(6 * H, 16, device=dev)
                 for d in (0, 1):
                     sh = -1 if d == 0 else 1
