@@ -67,9 +67,10 @@ class Decoder(nn.Module):
         for h in (self.class_head, self.pos_head, self.size_head, self.orient_head, self.valid_head):
             heads += [h.weight, h.bias]
         fn = F_.DecoderFn
-        # bf16 mode: tensor-core decoder from 256 traces up.  Below that the GEMMs are latency-bound anyway and a single
-        # bf16-induced ReLU flip moves the gradient of a 3-trace batch by several per cent (tools/bf16_err_probe.py).
-        if self.precision == "bf16" and latent.shape[0] >= 256 and latent.shape[1] % 64 == 0 \
+        # bf16 mode: tensor-core decoder for inference (any batch: predictions must not depend on the chunking) and for
+        # training from 256 traces up.  Below that the training GEMMs are latency-bound anyway and a single bf16-induced
+        # ReLU flip moves the gradient of a 3-trace batch by several per cent (tools/bf16_err_probe.py).
+        if self.precision == "bf16" and (latent.shape[0] >= 256 or not torch.is_grad_enabled()) and latent.shape[1] % 64 == 0 \
                 and self.trunk[0].out_features % 128 == 0 and self.trunk[2].out_features % 128 == 0:
             from .functional_bf16 import DecoderBF16Fn as fn
         cls, pos, size, orient, valid = fn.apply(
