@@ -153,6 +153,15 @@ int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
                     int B, int T, void* stream);
 
+/* ---- on-GPU trace preprocessing (replaces src/benchmark/dataloader.py:410-457 _process_traces
+ *      = src/benchmark/inference.py:24-57 process_traces, plus the padding of collate_fn dataloader.py:510-559) ------ */
+/* pts: [total, 4] fp32 rows (x, y, z, timestamp), the B traces back to back, each sorted by timestamp; offsets: [B+1]
+ * int64 (device).  feats: [B, out_len, 11] = x, y, z, t - t0, vx, vy, vz, ax, ay, az, speed; rows past a trace's length
+ * are zero; traces longer than max_len are down-sampled with numpy's linspace indices; mask: [B, out_len] uint8;
+ * lengths: [B] int64; unsorted_flag: one int set to 1 if a timestamp decreases.  Bit-identical to the numpy reference. */
+int rs_trace_features(const float* pts, const int64_t* offsets, int B, int max_len, int out_len, float* feats,
+                      unsigned char* mask, int64_t* lengths, int* unsorted_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

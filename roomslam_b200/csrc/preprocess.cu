@@ -1,0 +1,121 @@
+// On-GPU trace preprocessing: the 11-D kinematic features the shipped pipeline computes in
+// numpy per item and per epoch: src/benchmark/dataloader.py:410-457 (_process_traces) = src/benchmark/inference.py:24-57
+// (process_traces), followed by the pad-to-batch-max collate of dataloader.py:510-559.
+//
+//   a[i]    = (x, y, z, t - t_0)                    fp32
+//   diff[i] = a[i] - a[i-1]   (diff[0] = 0)         np.diff(..., prepend=first row)
+//   dt[i]   = max(diff_t[i], 1e-3f)                 np.clip(diffs[:, 3], 1e-3, None)
+//   vel[i]  = diff_xyz[i] / dt[i]                   IEEE fp32 division
+//   acc[i]  = vel[i] - vel[i-1]   (acc[0] = 0)
+//   speed[i]= sqrt((vx^2 + vy^2) + vz^2)            np.linalg.norm(vel, axis=1): products, left-to-right adds, sqrt
+//   row     = [x, y, z, t, vx, vy, vz, ax, ay, az, speed]
+//   traces longer than max_len keep the rows idx[j] = (int)(j * ((N-1)/(max_len-1))) in float64, idx[last] = N-1
+//   (np.linspace(0, N-1, max_len, dtype=int)); an empty trace yields one zero row.
+// Every operation is an explicit round-to-nearest intrinsic and the file is compiled with -fmad=false: the result is
+// bit-identical to the numpy reference.  One thread per output row (a row needs the three source points i-2 .. i,
+// served by L1), rows staged in shared memory and written back as contiguous 16-byte stores.
+#include "common.cuh"
+#include "../../include/roomslam_b200.h"
+
+namespace {
+
+struct P4 { float x, y, z, t; };
+
+__device__ __forceinline__ P4 load_norm(const float4* pts, long long i, float t0) {
+    const float4 v = __ldg(pts + i);
+    P4 p; p.x = v.x; p.y = v.y; p.z = v.z; p.t = __fsub_rn(v.w, t0);
+    return p;
+}
+
+__device__ __forceinline__ void velocity(const P4& a, const P4& b, bool first, float* v) {   // vel at the point a (b = previous)
+    const float dx = first ? 0.0f : __fsub_rn(a.x, b.x), dy = first ? 0.0f : __fsub_rn(a.y, b.y);
+    const float dz = first ? 0.0f : __fsub_rn(a.z, b.z), dtr = first ? 0.0f : __fsub_rn(a.t, b.t);
+    const float dt = fmaxf(dtr, 1e-3f);
+    v[0] = __fdiv_rn(dx, dt); v[1] = __fdiv_rn(dy, dt); v[2] = __fdiv_rn(dz, dt);
+}
+
+__global__ void __launch_bounds__(256)
+trace_features_kernel(const float4* __restrict__ pts, const long long* __restrict__ offsets, int B, int max_len, int out_len,
+                      float* __restrict__ feats, unsigned char* __restrict__ mask, long long* __restrict__ lengths,
+                      int* __restrict__ unsorted_flag, int vec_ok) {
+    __shared__ __align__(16) float rows[256 * 11];               // one chunk of 256 output rows, stored coalesced below
+    const long long total = (long long)B * out_len;
+    const long long chunks = (total + 255) / 256;
+    for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+        const long long e = c * 256 + threadIdx.x;
+        if (e < total) {
+            const int b = (int)(e / out_len), j = (int)(e % out_len);
+            const long long o0 = offsets[b];
+            const long long N = offsets[b + 1] - o0;
+            const long long L = N == 0 ? 1 : (N > max_len ? max_len : N);
+            if (j == 0) lengths[b] = L;
+            float row[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) row[k] = 0.0f;
+            const bool valid = j < L;
+            if (valid && N > 0) {
+                long long i = j;
+                if (N > max_len) {
+                    const double step = __ddiv_rn((double)(N - 1), (double)(max_len - 1));
+                    i = (j == max_len - 1) ? (N - 1) : (long long)__dmul_rn((double)j, step);
+                }
+                const float t0 = __ldg(pts + o0).w;
+                const P4 a = load_norm(pts, o0 + i, t0);
+                float v[3] = {0.f, 0.f, 0.f}, vp[3] = {0.f, 0.f, 0.f};
+                if (i >= 1) {
+                    const P4 p1 = load_norm(pts, o0 + i - 1, t0);
+                    velocity(a, p1, false, v);
+                    if (__ldg(pts + o0 + i).w < __ldg(pts + o0 + i - 1).w) *unsorted_flag = 1;
+                    if (i >= 2) {
+                        const P4 p2 = load_norm(pts, o0 + i - 2, t0);
+                        velocity(p1, p2, false, vp);
+                    }                                        // i == 1: vel[0] = 0 / dt = 0
+                }
+                row[0] = a.x; row[1] = a.y; row[2] = a.z; row[3] = a.t;
+                row[4] = v[0]; row[5] = v[1]; row[6] = v[2];
+                row[7] = (i >= 1) ? __fsub_rn(v[0], vp[0]) : 0.0f;
+                row[8] = (i >= 1) ? __fsub_rn(v[1], vp[1]) : 0.0f;
+                row[9] = (i >= 1) ? __fsub_rn(v[2], vp[2]) : 0.0f;
+                row[10] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+            }
+#pragma unroll
+            for (int k = 0; k < 11; ++k) rows[threadIdx.x * 11 + k] = row[k];    // stride 11 words: conflict-free
+            mask[e] = valid ? 1 : 0;
+        }
+        __syncthreads();
+        const long long nrows = (total - c * 256 < 256) ? (total - c * 256) : 256;
+        const int nfl = (int)nrows * 11;
+        float* dst = feats + c * 256 * 11;                       // 256 * 44 B per chunk: 16-byte aligned when feats is
+        if (vec_ok) {
+            for (int q = threadIdx.x; q < nfl / 4; q += 256)
+                reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(rows)[q];
+            for (int q = (nfl & ~3) + threadIdx.x; q < nfl; q += 256) dst[q] = rows[q];
+        } else {
+            for (int q = threadIdx.x; q < nfl; q += 256) dst[q] = rows[q];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int rs_trace_features(const float* pts, const int64_t* offsets, int B, int max_len, int out_len, float* feats,
+                                 unsigned char* mask, int64_t* lengths, int* unsorted_flag, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(offsets && feats && mask && lengths && unsorted_flag, "rs_trace_features: null pointer");
+    RS_REQUIRE(B >= 0 && max_len >= 2 && out_len >= 1, "rs_trace_features: need max_len >= 2 and out_len >= 1");
+    RS_REQUIRE((reinterpret_cast<uintptr_t>(pts) & 15) == 0, "rs_trace_features: points must be 16-byte aligned (x, y, z, t rows)");
+    RS_CUDA_OK(cudaMemsetAsync(unsorted_flag, 0, sizeof(int), stream));
+    const long long total = (long long)B * out_len;
+    if (total == 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;                       // 8 resident CTAs per SM, chunk-strided
+    const int vec_ok = (reinterpret_cast<uintptr_t>(feats) & 15) == 0;
+    trace_features_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(pts),
+                                                           reinterpret_cast<const long long*>(offsets), B, max_len, out_len, feats,
+                                                           mask, reinterpret_cast<long long*>(lengths), unsorted_flag, vec_ok);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,76 @@
+"""On-GPU trace preprocessing: raw (x, y, z, timestamp) points -> padded (B, W, 11) kinematic features + mask.
+
+Mirrors, for a whole batch in one launch, what the upstream pipeline does per item on the host in numpy:
+``process_traces`` (src/benchmark/inference.py:24-57, same body in src/benchmark/dataloader.py:410-457) followed by the
+padding of ``collate_fn`` (src/benchmark/dataloader.py:510-559).  Bit-identical to the numpy code (rs_trace_features).
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FEATURES = ("x", "y", "z", "t", "vx", "vy", "vz", "ax", "ay", "az", "speed")
+
+
+def pack_traces(traces: Sequence, device="cuda") -> tuple[torch.Tensor, torch.Tensor]:
+    """List of (N_i, 4) arrays / tensors (rows x, y, z, timestamp) -> packed (total, 4) fp32 on `device`, offsets (B+1) int64 (CPU)."""
+    parts, offs = [], [0]
+    for t in traces:
+        t = torch.as_tensor(np.asarray(t, dtype=np.float32) if not torch.is_tensor(t) else t, dtype=torch.float32).reshape(-1, 4)
+        parts.append(t)
+        offs.append(offs[-1] + t.shape[0])
+    packed = torch.cat(parts) if parts else torch.zeros(0, 4)
+    return packed.to(device, non_blocking=True).contiguous(), torch.tensor(offs, dtype=torch.int64)
+
+
+def sort_by_time(packed: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    """Orders every trace by timestamp (inference.py:38-39).  Ties keep their input order (numpy's argsort leaves them
+    unspecified)."""
+    if packed.shape[0] == 0:
+        return packed
+    counts = (offsets[1:] - offsets[:-1]).to(packed.device)
+    seg = torch.repeat_interleave(torch.arange(counts.numel(), device=packed.device), counts)
+    by_t = torch.sort(packed[:, 3], stable=True).indices
+    order = by_t[torch.sort(seg[by_t], stable=True).indices]
+    return packed[order].contiguous()
+
+
+def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3000, sort: bool = True,
+                   check_sorted: bool = False) -> dict:
+    """traces: list of (N_i, 4) arrays, or a packed (total, 4) CUDA tensor with `offsets` (B+1 int64).
+
+    Returns {"traces": (B, W, 11) fp32, "trace_mask": (B, W) bool, "lengths": (B,) int64}, W = max_i min(N_i, max_len)
+    (an empty trace gives one zero row, like the reference) -- the keys collate_fn emits (dataloader.py:549-551).
+    """
+    if offsets is None:
+        packed, offsets = pack_traces(traces)
+    else:
+        packed = traces
+    if not packed.is_cuda:
+        raise _lib.RoomSlamError("trace_features: the points must be on a CUDA device (there is no CPU path)")
+    if max_len < 2:
+        raise ValueError("max_len must be >= 2")
+    packed = packed.contiguous()
+    host_off = offsets.cpu()
+    B = host_off.numel() - 1
+    counts = host_off[1:] - host_off[:-1]
+    if B > 0 and (int(counts.min()) < 0 or int(host_off[-1]) != packed.shape[0] or int(host_off[0]) != 0):
+        raise ValueError("offsets must start at 0, be non-decreasing and end at the number of points")
+    width = int(torch.clamp(counts, 1, max_len).max()) if B > 0 else 1
+    if sort:
+        packed = sort_by_time(packed, host_off)
+    dev = packed.device
+    feats = torch.empty(B, width, 11, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, width, dtype=torch.uint8, device=dev)
+    lengths = torch.empty(B, dtype=torch.int64, device=dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    dev_off = host_off.to(dev, non_blocking=True)
+    _lib.call("rs_trace_features", packed.data_ptr(), dev_off.data_ptr(), B, max_len, width, feats.data_ptr(),
+              mask.data_ptr(), lengths.data_ptr(), flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if check_sorted and int(flag.item()):
+        raise ValueError("trace_features: a trace is not sorted by timestamp (pass sort=True)")
+    return {"traces": feats, "trace_mask": mask.bool(), "lengths": lengths}
