@@ -162,6 +162,37 @@ int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, co
 int rs_trace_features(const float* pts, const int64_t* offsets, int B, int max_len, int out_len, float* feats,
                       unsigned char* mask, int64_t* lengths, int* unsorted_flag, void* stream);
 
+/* ---- the shipped BiLSTM + query-decoder model (src/benchmark/model.py:6-153), fp32 ------------ */
+/* One bidirectional LSTM layer (replaces torch.nn.LSTM, model.py:16-23,49).  P: [.., 2*4H] = W_ih x + b_ih + b_hh for both
+ * directions (gate rows i|f|g|o); w_hh_t: [2][H][4H]; out: [.., 2H]; saved: [2][B][T][5][H] (i, f, g, o, c) or NULL. */
+int rs_lstm_fwd_f32(const float* P, int64_t p_ld, int64_t p_rows, int64_t p_row0, const float* w_hh_t, float* out,
+                    int64_t o_ld, int64_t o_rows, int64_t o_row0, float* saved, int B, int T, int H, void* stream);
+/* w_hh: [2][4H][H]; dG: [.., 2*4H] gradient w.r.t. the gate pre-activations. */
+int rs_lstm_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows, int64_t do_row0, const float* saved,
+                    const float* w_hh, float* dG, int64_t g_ld, int64_t g_rows, int64_t g_row0, int B, int T, int H,
+                    void* stream);
+/* Per-trace normaliser (model.py:38-46): mean [B,3] of the valid (x, y, z), rms [B] of the centred (x, z) (floor 1e-3),
+ * count [B] = max(valid tokens, 1).  traces: [B, N, F]; mask: [B, N] uint8 or NULL. */
+int rs_trace_stats_f32(const float* traces, int F, const unsigned char* mask, int B, int N, float* mean, float* rms,
+                       float* count, void* stream);
+/* Query attention of SimpleQueryDecoder.forward (model.py:86-127) with the k/v projections folded into the query side:
+ * scores = qk . m + qb (qk: [Q, D], qb: [Q], temperature and 1/sqrt(D) already applied), softmax over the valid tokens,
+ * ctx [B,Q,D] = attn . memory, anchor [B,Q,3] = attn . (xyz - mean) / rms, summary [B,D] = masked mean of memory,
+ * stats [B,Q,2] = softmax (max, sum).  workspace: rs_query_attn_workspace(B, Q, D, splits) floats. */
+int64_t rs_query_attn_workspace(int B, int Q, int D, int splits);
+int rs_query_attn_fwd_f32(const float* memory, int64_t m_ld, int64_t m_rows, int64_t m_row0, const float* traces, int F,
+                          const unsigned char* mask, const float* mean, const float* rms, const float* qk, const float* qb,
+                          int B, int N, int Q, int D, int splits, float* workspace, float* ctx, float* anchor,
+                          float* summary, float* stats, void* stream);
+/* d_memory: written ([.., D] rows; must be zero-filled when Q > 32); dq_part: [B*splits][Q][D+1] partial gradients of
+ * (qk | qb), to be summed over the first axis. */
+int rs_query_attn_bwd_f32(const float* memory, int64_t m_ld, int64_t m_rows, int64_t m_row0, const float* traces, int F,
+                          const unsigned char* mask, const float* mean, const float* rms, const float* count,
+                          const float* qk, const float* qb, const float* ctx, const float* anchor, const float* stats,
+                          const float* d_ctx, const float* d_anchor, const float* d_summary, int B, int N, int Q, int D,
+                          int splits, float* d_memory, int64_t dm_ld, int64_t dm_rows, int64_t dm_row0, float* dq_part,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
