@@ -164,9 +164,10 @@ int rs_trace_features(const float* pts, const int64_t* offsets, int B, int max_l
 
 /* ---- the shipped BiLSTM + query-decoder model (src/benchmark/model.py:6-153), fp32 ------------ */
 /* One bidirectional LSTM layer (replaces torch.nn.LSTM, model.py:16-23,49).  P: [.., 2*4H] = W_ih x + b_ih + b_hh for both
- * directions (gate rows i|f|g|o); w_hh_t: [2][H][4H]; out: [.., 2H]; saved: [2][B][T][5][H] (i, f, g, o, c) or NULL. */
-int rs_lstm_fwd_f32(const float* P, int64_t p_ld, int64_t p_rows, int64_t p_row0, const float* w_hh_t, float* out,
-                    int64_t o_ld, int64_t o_rows, int64_t o_row0, float* saved, int B, int T, int H, void* stream);
+ * directions (gate rows i|f|g|o); w_hh: [2][4H][H] and its transpose w_hh_t: [2][H][4H]; out: [.., 2H]; saved: [2][B][T][5][H] (i, f, g, o, c) or NULL. */
+int rs_lstm_fwd_f32(const float* P, int64_t p_ld, int64_t p_rows, int64_t p_row0, const float* w_hh, const float* w_hh_t,
+                    float* out, int64_t o_ld, int64_t o_rows, int64_t o_row0, float* saved, int B, int T, int H,
+                    void* stream);
 /* w_hh: [2][4H][H]; dG: [.., 2*4H] gradient w.r.t. the gate pre-activations. */
 int rs_lstm_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows, int64_t do_row0, const float* saved,
                     const float* w_hh, float* dG, int64_t g_ld, int64_t g_rows, int64_t g_row0, int B, int T, int H,

@@ -86,7 +86,7 @@ class LSTMLayerFn(torch.autograd.Function):
         out = padded(B, T, 2 * H, dev)
         saved = torch.empty(2, B, T, 5, H, device=dev) if need_grad else None
         with ktime("lstm_fwd_f32_kernel", 2.0 * B * T * 2 * 4 * H * H):
-            _lib.call("rs_lstm_fwd_f32", _p(P), 8 * H, Tp, 1, _p(w_hh_t), _p(out), 2 * H, Tp, 1, _p(saved), B, T, H, st)
+            _lib.call("rs_lstm_fwd_f32", _p(P), 8 * H, Tp, 1, _p(w_hh_cat), _p(w_hh_t), _p(out), 2 * H, Tp, 1, _p(saved), B, T, H, st)
         del P
         ctx.dims = (B, T, I, H)
         ctx.mask = mask
