@@ -194,6 +194,22 @@ int rs_query_attn_bwd_f32(const float* memory, int64_t m_ld, int64_t m_rows, int
                           int splits, float* d_memory, int64_t dm_ld, int64_t dm_rows, int64_t dm_row0, float* dq_part,
                           void* stream);
 
+/* ---- batched Hungarian matching + set loss (src/benchmark/train.py:14-187) ------------------- */
+/* pred_boxes [B,Q,6], pred_logits [B,Q,4], gt_boxes [B,M,6], gt_labels [B,M] int64, gt_valid [B,M] uint8 (Q <= 128,
+ * M <= 64).  cost = w_class * (-softmax(logits)[label]) + w_box * L1(box) over the valid colliders (train.py:44-53);
+ * optimal assignment per sample (= scipy.optimize.linear_sum_assignment, train.py:57).  Outputs, K = min(Q, M) per
+ * sample, pairs ordered by query index, -1 padded: match_pred [B,K] query index, match_slot [B,K] collider slot,
+ * match_rank [B,K] index among the sample's valid colliders (the reference's gt_idx), n_match [B]. */
+int rs_hungarian_match(const float* pred_boxes, const float* pred_logits, const float* gt_boxes, const int64_t* gt_labels,
+                       const unsigned char* gt_valid, int B, int Q, int M, float w_class, float w_box, int* match_pred,
+                       int* match_slot, int* match_rank, int* n_match, void* stream);
+/* SetCriterion.forward (train.py:109-187) on the matched pairs: losses[4] = cross-entropy, L1, 1 - GIoU (each a mean over
+ * the batch-wide pairs) and the weighted total; g_logits [B,Q,4], g_l1 [B,Q,6], g_giou [B,Q,6] = gradients of the three
+ * unweighted losses w.r.t. the predictions (zero for unmatched queries).  workspace: 1 + 3*B floats. */
+int rs_set_loss_f32(const float* pred_boxes, const float* pred_logits, const float* gt_boxes, const int64_t* gt_labels, int B,
+                    int Q, int M, const int* match_pred, const int* match_slot, const int* n_match, float w_class, float w_l1,
+                    float w_giou, float* workspace, float* losses, float* g_logits, float* g_l1, float* g_giou, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
