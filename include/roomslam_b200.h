@@ -210,6 +210,23 @@ int rs_set_loss_f32(const float* pred_boxes, const float* pred_logits, const flo
                     int Q, int M, const int* match_pred, const int* match_slot, const int* n_match, float w_class, float w_l1,
                     float w_giou, float* workspace, float* losses, float* g_logits, float* g_l1, float* g_giou, void* stream);
 
+/* ---- batched evaluation (src/benchmark/train.py:234-328, src/benchmark/inference.py:60-170) ---- */
+/* counts[7] (double, device) += [sum of matched IoUs, matched pairs, TP (IoU >= thr), FP, FN (valid colliders without a
+ * match), class hits, class total] of this batch; matches from rs_hungarian_match.  workspace: 7*B doubles. */
+int rs_eval_pairs(const float* pred_boxes, const float* pred_logits, const float* gt_boxes, const int64_t* gt_labels,
+                  const unsigned char* gt_valid, int B, int Q, int M, const int* match_pred, const int* match_slot,
+                  const int* n_match, float iou_thresh, double* workspace, double* counts, void* stream);
+/* post_process_predictions (inference.py:130-170): confidence = max softmax > conf_thr, then per-class greedy NMS (a box
+ * is dropped when its IoU with a kept, more confident box of its class is >= nms_thr).  keep_idx [B,Q]: kept query
+ * indices in the reference's output order (class 0..3, descending confidence), -1 padded; n_keep [B]; conf, label [B,Q]. */
+int rs_nms_3d(const float* pred_boxes, const float* pred_logits, int B, int Q, float conf_thr, float nms_thr, int* keep_idx,
+              int* n_keep, float* conf, int* label, void* stream);
+/* True-positive flags for mAP: per scene, predictions in descending confidence claim the best-IoU unclaimed valid collider
+ * of their predicted class; flag = 1 when that IoU >= iou_thr.  n_gt[4] += colliders per class. */
+int rs_ap_flags(const float* pred_boxes, const float* pred_logits, const float* gt_boxes, const int64_t* gt_labels,
+                const unsigned char* gt_valid, int B, int Q, int M, float iou_thr, int* flags, float* conf, int* label, int* n_gt,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "--expt-relaxed-constexpr", "-I", INCLUDE]
 # per-file extras: the binning TU must never contract mul+add into an FMA (bit-exact with the oracle)
-EXTRA = {"heatmap.cu": ["-fmad=false"], "preprocess.cu": ["-fmad=false"]}
+EXTRA = {"heatmap.cu": ["-fmad=false"], "preprocess.cu": ["-fmad=false"], "eval.cu": ["-fmad=false"]}
 
 
 def nvcc() -> str:

@@ -33,7 +33,7 @@ def test_against_reference_golden(name):
     losses = crit({"pred_boxes": boxes, "pred_classes": logits}, tg)
     for k in ("class_loss", "l1_loss", "giou_loss", "total_loss"):
         want = float(golden[f"{name}_{k}"])
-        assert abs(float(losses[k]) - want) <= 1e-5 * max(1.0, abs(want)), k
+        assert abs(float(losses[k].detach()) - want) <= 1e-5 * max(1.0, abs(want)), k
     losses["total_loss"].backward()
     np.testing.assert_allclose(boxes.grad.cpu().numpy(), golden[f"{name}_dboxes"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(logits.grad.cpu().numpy(), golden[f"{name}_dlogits"], rtol=1e-4, atol=1e-6)
