@@ -362,6 +362,152 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# --suite next: the SURVEY.md 8(f) rows (preprocessing, shipped BiLSTM model, Hungarian set loss, evaluation), each
+# timed on the GPU with the CPU oracle beside it.  One JSON line per row; not part of the default run.
+# ------------------------------------------------------------------------------------------------------------
+def _time_gpu(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _time_cpu(fn, reps=1):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def run_next_rows(args):
+    import numpy as np
+    from roomslam_b200 import _lib, preprocess
+    from roomslam_b200.evaluation import MetricAccumulator, mean_average_precision, nms_batch
+    from roomslam_b200.lstm_model import TraceToColliderLSTM
+    from roomslam_b200.set_loss import SetCriterion
+    from oracle import eval_ref, features_ref, set_loss_ref
+    from oracle.lstm_ref import TraceToColliderLSTMRef
+    _lib.load()
+    torch.cuda.set_device(0)
+    pk = peaks()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    W = {"class_loss": 2.0, "l1_loss": 5.0, "giou_loss": 2.0}
+
+    # ---- row 1: trace preprocessing, 4096 traces x 3000 points ----
+    B, N = 4096, 3000
+    pts = torch.randn(B, N, 4, generator=g)
+    pts[..., 3] = torch.cumsum(torch.rand(B, N, generator=g) * 0.1 + 1e-3, 1)
+    flat, off = pts.reshape(-1, 4).cuda(), torch.arange(B + 1, dtype=torch.int64) * N
+    dev_off = off.cuda()
+    feats = torch.empty(B, N, 11, device="cuda"); mask = torch.empty(B, N, dtype=torch.uint8, device="cuda")
+    lens = torch.empty(B, dtype=torch.int64, device="cuda"); flag = torch.empty(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ms_k = _time_gpu(lambda: _lib.call("rs_trace_features", flat.data_ptr(), dev_off.data_ptr(), B, 3000, N, feats.data_ptr(),
+                                       mask.data_ptr(), lens.data_ptr(), flag.data_ptr(), st), args.steps * 4, 3)
+    ms_api = _time_gpu(lambda: preprocess.trace_features(flat, off, max_len=3000), args.steps, 3)
+    sample = [pts[b].numpy() for b in range(64)]
+    t_cpu = _time_cpu(lambda: [features_ref.process_points(p) for p in sample])
+    gbs = B * N * 61 / ms_k / 1e6
+    print(json.dumps({"row": "8(f)1 trace preprocessing", "metric": "Gpoints/s", "value": round(B * N / ms_k / 1e6, 2),
+                      "value_api": round(B * N / ms_api / 1e6, 2), "ms_kernel": round(ms_k, 4), "dtype": "f32",
+                      "config": {"workload": f"{B} traces x {N} points -> (B, 3000, 11) features + mask"},
+                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": round(gbs / pk["hbm_gbs"], 3), "traffic": None, "bytes_per_point": 61},
+                      "cpu_baseline": {"value": round(64 * N / t_cpu / 1e9, 5), "unit": "Gpoints/s", "cores": 1, "kind": "port",
+                                       "sample": "64 traces x 3000 points, numpy oracle"}}), flush=True)
+
+    # ---- row 2 + 3: shipped BiLSTM model + Hungarian set loss, forward + backward ----
+    for B in (20, 256):
+        N, Q, M = 3000, 30, 50
+        model = TraceToColliderLSTM(128, Q).cuda().train()
+        model.encoder.dropout = 0.0
+        x = torch.randn(B, N, 11, generator=g).cuda()
+        tmask = torch.ones(B, N, dtype=torch.bool, device="cuda")
+        tg = {"boxes": torch.cat([torch.randn(B, M, 3, generator=g), torch.rand(B, M, 3, generator=g) + 0.2], -1).cuda(),
+              "labels": torch.randint(0, 4, (B, M), generator=g).cuda(), "valid_mask": (torch.rand(B, M, generator=g) < 0.3).cuda()}
+        crit = SetCriterion(W)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            crit(model(x, tmask), tg)["total_loss"].backward()
+        ms = _time_gpu(step, args.steps, 3)
+        line = {"row": "8(f)2+3 BiLSTM query-decoder model + Hungarian set loss, fwd+bwd", "metric": "train traces/s",
+                "value": round(B / ms * 1e3, 1), "ms_per_step": round(ms, 2), "dtype": "f32",
+                "config": {"workload": f"batch {B} x {N} points, d_model 128, 30 queries, 50 collider slots"}}
+        if B == 20:
+            ref = TraceToColliderLSTMRef(128, Q).train()
+            ref.encoder.lstm.dropout = 0.0
+            xc, mc = x[:4].cpu(), tmask[:4].cpu()
+            tc = {k: v[:4].cpu() for k, v in tg.items()}
+
+            def cpu_step():
+                ref.zero_grad()
+                set_loss_ref.set_loss(ref(xc, mc), tc)[0]["total_loss"].backward()
+            t_cpu = _time_cpu(cpu_step)
+            line["cpu_baseline"] = {"value": round(4 / t_cpu, 2), "unit": "train traces/s", "cores": cores, "kind": "port",
+                                    "sample": "batch 4 x 3000 points, torch CPU oracle + scipy matcher"}
+        print(json.dumps(line), flush=True)
+
+    # ---- row 3 alone and row 4: 4096 scenes ----
+    B, Q, M = 4096, 30, 50
+    gt = torch.cat([torch.randn(B, M, 3, generator=g) * 3, torch.rand(B, M, 3, generator=g) * 2 + 0.3], -1)
+    valid = torch.rand(B, M, generator=g) < 0.4
+    labels = torch.randint(0, 4, (B, M), generator=g)
+    boxes = gt[:, :Q] + torch.randn(B, Q, 6, generator=g) * 0.12
+    boxes[..., 3:] = boxes[..., 3:].clamp_min(0.05)
+    logits = torch.randn(B, Q, 4, generator=g) * 2
+    cb, cl = boxes.cuda().requires_grad_(True), logits.cuda().requires_grad_(True)
+    tg = {"boxes": gt.cuda(), "labels": labels.cuda(), "valid_mask": valid.cuda()}
+    crit = SetCriterion(W)
+
+    def loss_step():
+        cb.grad = None; cl.grad = None
+        crit({"pred_boxes": cb, "pred_classes": cl}, tg)["total_loss"].backward()
+    ms = _time_gpu(loss_step, args.steps * 4, 3)
+    S = 256
+    bs, ls = boxes[:S].clone().requires_grad_(True), logits[:S].clone().requires_grad_(True)
+    ts = {"boxes": gt[:S], "labels": labels[:S], "valid_mask": valid[:S]}
+    t_cpu = _time_cpu(lambda: set_loss_ref.set_loss({"pred_boxes": bs, "pred_classes": ls}, ts)[0]["total_loss"].backward())
+    print(json.dumps({"row": "8(f)3 Hungarian matcher + set loss, fwd+bwd", "metric": "scenes/s", "value": round(B / ms * 1e3, 0),
+                      "ms_per_step": round(ms, 3), "dtype": "f32 cost / f64 solver",
+                      "config": {"workload": f"{B} scenes x {Q} queries x {M} collider slots (40% valid)"},
+                      "cpu_baseline": {"value": round(S / t_cpu, 0), "unit": "scenes/s", "cores": cores, "kind": "port",
+                                       "sample": f"{S} scenes, torch CPU + scipy.optimize.linear_sum_assignment"}}), flush=True)
+
+    def eval_step():
+        acc = MetricAccumulator("cuda")
+        acc.update({"pred_boxes": cb, "pred_classes": cl}, tg)
+        nms_batch(cb, cl)
+        return acc.compute(), mean_average_precision(cb, cl, tg["boxes"], tg["labels"], tg["valid_mask"])[0]
+    ms = _time_gpu(eval_step, args.steps, 3)
+    S = 64
+    o = {"pred_boxes": boxes[:S], "pred_classes": logits[:S]}
+    ts = {"boxes": gt[:S], "labels": labels[:S], "valid_mask": valid[:S]}
+
+    def cpu_eval():
+        eval_ref.metrics_from_counts(eval_ref.batch_counts(o, ts))
+        for b in range(S):
+            eval_ref.nms_order(boxes[b], logits[b])
+        eval_ref.mean_average_precision(boxes[:S], logits[:S], gt[:S], labels[:S], valid[:S])
+    t_cpu = _time_cpu(cpu_eval)
+    print(json.dumps({"row": "8(f)4 evaluation: matched metrics + NMS + mAP (incl. the host read of the results)",
+                      "metric": "scenes/s", "value": round(B / ms * 1e3, 0), "ms_per_step": round(ms, 3), "dtype": "f32",
+                      "config": {"workload": f"{B} scenes x {Q} queries x {M} collider slots"},
+                      "cpu_baseline": {"value": round(S / t_cpu, 1), "unit": "scenes/s", "cores": 1, "kind": "port",
+                                       "sample": f"{S} scenes, python/numpy oracle"}}), flush=True)
+
+
+
 def train_roofline(kernel_ms, B, pk, precision):
     """Roofline object for the kernel with the largest share of the training step."""
     if not kernel_ms:
@@ -387,7 +533,11 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="traces per GPU")
     ap.add_argument("--heatmap-traces", type=int, default=HEATMAP_TRACES, help="traces per GPU")
+    ap.add_argument("--suite", default="headline", choices=["headline", "next"],
+                    help="'next': one JSON line per SURVEY.md 8(f) row instead of the headline line (single GPU)")
     args = ap.parse_args()
+    if args.suite == "next":
+        return run_next_rows(args)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

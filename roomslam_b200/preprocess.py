@@ -39,9 +39,13 @@ def sort_by_time(packed: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
     return packed[order].contiguous()
 
 
-def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3000, sort: bool = True,
+def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3000, sort="auto",
                    check_sorted: bool = False) -> dict:
     """traces: list of (N_i, 4) arrays, or a packed (total, 4) CUDA tensor with `offsets` (B+1 int64).
+
+    sort: "auto" (default) runs the kernel on the input order and re-runs it on time-sorted points only if the kernel saw
+    a decreasing timestamp (recorded traces are already ordered; the two device sorts cost ~40x the kernel);
+    True always sorts (the reference's unconditional argsort, inference.py:38-39); False never does.
 
     Returns {"traces": (B, W, 11) fp32, "trace_mask": (B, W) bool, "lengths": (B,) int64}, W = max_i min(N_i, max_len)
     (an empty trace gives one zero row, like the reference) -- the keys collate_fn emits (dataloader.py:549-551).
@@ -61,7 +65,7 @@ def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3
     if B > 0 and (int(counts.min()) < 0 or int(host_off[-1]) != packed.shape[0] or int(host_off[0]) != 0):
         raise ValueError("offsets must start at 0, be non-decreasing and end at the number of points")
     width = int(torch.clamp(counts, 1, max_len).max()) if B > 0 else 1
-    if sort:
+    if sort is True:
         packed = sort_by_time(packed, host_off)
     dev = packed.device
     feats = torch.empty(B, width, 11, dtype=torch.float32, device=dev)
@@ -71,6 +75,8 @@ def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3
     dev_off = host_off.to(dev, non_blocking=True)
     _lib.call("rs_trace_features", packed.data_ptr(), dev_off.data_ptr(), B, max_len, width, feats.data_ptr(),
               mask.data_ptr(), lengths.data_ptr(), flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if sort == "auto" and int(flag.item()):
+        return trace_features(sort_by_time(packed, host_off), host_off, max_len, sort=False, check_sorted=check_sorted)
     if check_sorted and int(flag.item()):
         raise ValueError("trace_features: a trace is not sorted by timestamp (pass sort=True)")
     return {"traces": feats, "trace_mask": mask.bool(), "lengths": lengths}

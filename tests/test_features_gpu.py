@@ -92,3 +92,12 @@ def test_large_batch_property():
     acc = torch.zeros_like(v); acc[:, 1:] = v[:, 1:] - v[:, :-1]
     assert torch.equal(f[..., 7:10], acc)
     torch.testing.assert_close(f[..., 10], v.norm(dim=-1), rtol=1e-6, atol=0)
+
+
+def test_auto_sort_only_when_needed(golden):
+    from roomslam_b200 import preprocess
+    pts = golden["unsorted_points"]
+    auto = preprocess.trace_features([pts, golden["two_points"]], max_len=3000)            # default sort="auto"
+    want, wmask = features_ref.collate([features_ref.process_points(pts), features_ref.process_points(golden["two_points"])])
+    assert np.array_equal(bits(auto["traces"].cpu().numpy()), bits(want))
+    assert np.array_equal(auto["trace_mask"].cpu().numpy(), wmask)

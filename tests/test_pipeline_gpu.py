@@ -1,0 +1,52 @@
+"""GPU: the upstream training recipe end to end on the library (src/benchmark/train.py:190-232,440-444): raw points ->
+rs_trace_features -> BiLSTM query decoder -> Hungarian set loss -> backward -> clip -> AdamW; then evaluation."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_training_loop_reduces_the_set_loss_and_evaluates():
+    from roomslam_b200 import preprocess
+    from roomslam_b200.evaluation import MetricAccumulator, mean_average_precision, nms_batch
+    from roomslam_b200.lstm_model import build_model
+    from roomslam_b200.set_loss import SetCriterion
+    rng = np.random.default_rng(0)
+    traces = []
+    for n in (400, 777, 650, 512):                                    # ragged raw traces (x, y, z, timestamp)
+        t = np.cumsum(rng.uniform(0.01, 0.05, n))
+        traces.append(np.stack([np.cumsum(rng.normal(0, 0.03, n)), 1.6 + rng.normal(0, 0.01, n), np.cumsum(rng.normal(0, 0.03, n)), t], 1).astype(np.float32))
+    batch = preprocess.trace_features(traces, max_len=600)
+    x, mask = batch["traces"], batch["trace_mask"]
+    assert x.shape == (4, 600, 11) and mask.sum(1).tolist() == [400, 600, 600, 512]
+    B, M = 4, 50
+    g = torch.Generator().manual_seed(1)
+    gt = torch.cat([torch.randn(B, M, 3, generator=g), torch.rand(B, M, 3, generator=g) * 0.5 + 0.2], -1)
+    valid = torch.zeros(B, M, dtype=torch.bool); valid[:, :6] = True
+    targets = {"boxes": (gt * valid[..., None]).cuda(), "labels": torch.randint(0, 4, (B, M), generator=g).cuda(), "valid_mask": valid.cuda()}
+    torch.manual_seed(0)
+    model = build_model(num_queries=30, d_model=128, model_type="lstm", dropout=0.0).cuda().train()
+    crit = SetCriterion({"class_loss": 2.0, "l1_loss": 5.0, "giou_loss": 2.0})
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-3, weight_decay=1e-4)
+    first = last = None
+    for it in range(40):
+        opt.zero_grad()
+        losses = crit(model(x, mask), targets)
+        losses["total_loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        last = float(losses["total_loss"].detach())
+        first = last if first is None else first
+    assert np.isfinite(last) and last < 0.85 * first, (first, last)
+    model.eval()
+    with torch.no_grad():
+        out = model(x, mask)
+    acc = MetricAccumulator("cuda")
+    acc.update(out, targets)
+    m = acc.compute()
+    assert m["tp"] + m["fp"] == 24 and m["fn"] == 0 and 0.0 <= m["mIoU"] <= 1.0
+    keep, n, conf, label = nms_batch(out["pred_boxes"], out["pred_classes"])
+    assert keep.shape == (4, 30) and int(n.max()) <= 30
+    mAP, aps = mean_average_precision(out["pred_boxes"], out["pred_classes"], targets["boxes"], targets["labels"], targets["valid_mask"])
+    assert 0.0 <= mAP <= 1.0
