@@ -14,6 +14,8 @@
 //                 -> dW_ih, dW_hh (block of dG at t' paired with the block of h at t' -/+ 1), bias gradients (ones column)
 //
 // Warp roles: warp 0 = bulk-copy producer, warp 1 = tcgen05.mma issuer (one lane), warps 2..5 = TMEM epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/roomslam_b200.h"
 
@@ -176,6 +178,139 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_kernel(const NtPara
     rs::tc_fence_before();
     __syncthreads();
     if (warp == 1) rs::tmem_dealloc<256>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-resident variant for the input projection (K <= 256, N a multiple of 256).  The kernel above re-streams the
+// whole W (N x K: 384 KB for the layer-1 projection) through shared memory for EVERY 128-trace block: 448 KB of L2->SM
+// traffic and ~1.2 MB of shared-memory traffic per block against 786 KB the SM can move while the tensor core does the
+// block's 50 MFLOP -- shared-memory bandwidth, not HBM, bounds it.  Here a CTA owns ONE 256-column slice of W (128 KB,
+// loaded once, resident for the whole launch) and streams only the A blocks (64 KB each, 16 KB pieces through a ring);
+// the CTAs of a group (one per W slice) walk the same blocks at the same time, so A comes from HBM once and from L2 for
+// the other slices.  MMA shape 128 x 256 x 16; two 256-column accumulators (all 512 TMEM columns) overlap the
+// epilogue of one block with the MMAs of the next.
+constexpr int WRES_STAGES = 5;
+__global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_wres_kernel(const NtParams p, int n_parts) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;                                           // [k_blocks][8 chunks][256 rows][16 B]
+    uint8_t* stages = smem + p.k_blocks * 2 * PIECE_BYTES;         // ring of A pieces
+    float* bias_s = reinterpret_cast<float*>(stages + WRES_STAGES * PIECE_BYTES);   // [256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
+    uint64_t* full_bar = bars;                        // [WRES_STAGES]
+    uint64_t* empty_bar = bars + WRES_STAGES;         // [WRES_STAGES]
+    uint64_t* acc_full = bars + 2 * WRES_STAGES;      // [2]
+    uint64_t* acc_empty = bars + 2 * WRES_STAGES + 2; // [2]
+    uint64_t* w_full = bars + 2 * WRES_STAGES + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WRES_STAGES + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int part = blockIdx.x % n_parts, group = blockIdx.x / n_parts, groups = gridDim.x / n_parts;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < WRES_STAGES; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { rs::mbar_init(&acc_full[s], 1); rs::mbar_init(&acc_empty[s], 8); }
+        rs::mbar_init(w_full, 1);
+        rs::fence_mbar_init();
+    }
+    if (warp == 1) rs::tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < 256; i += NT_THREADS) bias_s[i] = p.bias ? p.bias[part * 256 + i] : 0.0f;
+    rs::tc_fence_before();
+    __syncthreads();
+    rs::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // W slice: the two 128-row pieces of every K block are interleaved chunk by chunk into 256-row chunk columns
+            rs::mbar_expect_tx(w_full, p.k_blocks * 2 * PIECE_BYTES);
+            for (int kb = 0; kb < p.k_blocks; ++kb)
+                for (int half = 0; half < 2; ++half) {
+                    const uint8_t* src = p.W + ((long long)(part * 2 + half) * p.k_blocks + kb) * PIECE_BYTES;
+                    for (int c = 0; c < 8; ++c)
+                        rs::bulk_load(w_s + kb * 2 * PIECE_BYTES + c * 2 * CHUNK_BYTES + half * CHUNK_BYTES, src + c * CHUNK_BYTES,
+                                      CHUNK_BYTES, w_full);
+                }
+            int stage = 0; uint32_t phase = 0;
+            for (int m = group; m < p.n_blocks; m += groups) {
+                const uint8_t* ablk = p.A + (long long)m * p.a_block_bytes;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    rs::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    rs::mbar_expect_tx(&full_bar[stage], PIECE_BYTES);
+                    rs::bulk_load(stages + stage * PIECE_BYTES, ablk + (long long)p.a_kchunk[kb] * CHUNK_BYTES, PIECE_BYTES, &full_bar[stage]);
+                    if (++stage == WRES_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = rs::umma_idesc_bf16(128, 256, 0, 0);
+        rs::mbar_wait(w_full, 0);
+        rs::tc_fence_after();
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t w_addr = rs::smem_u32(w_s);
+        for (int m = group; m < p.n_blocks; m += groups) {
+            rs::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            rs::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * 256;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                rs::mbar_wait(&full_bar[stage], phase);
+                rs::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = rs::smem_u32(stages + stage * PIECE_BYTES);
+                    const uint32_t sb = w_addr + kb * 2 * PIECE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = rs::umma_desc_noswz(sa + k * 2 * CHUNK_BYTES, CHUNK_BYTES, 128);
+                        const uint64_t db = rs::umma_desc_noswz(sb + k * 2 * (2 * CHUNK_BYTES), 2 * CHUNK_BYTES, 128);
+                        rs::tc_mma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+                    }
+                    rs::tc_commit(&empty_bar[stage]);
+                    if (kb == p.k_blocks - 1) rs::tc_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == WRES_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        const int q = warp & 3, row = q * 32 + lane;
+        const int chalf = (warp - 2) >> 2;              // which 128 of the slice's 256 columns this warp converts
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int m = group; m < p.n_blocks; m += groups) {
+            uint8_t* cblk = p.C + (long long)m * p.c_block_bytes + row * 16;
+            rs::mbar_wait(&acc_full[acc], acc_phase);
+            rs::tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256 + chalf * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t r[32];
+                rs::tmem_ld_32x32b_x32(taddr + c0, r);
+                rs::tmem_ld_wait();
+                const float* bs = bias_s + chalf * 128 + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t pk[4];
+                    const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float v0 = __uint_as_float(r[8 * j + 2 * e]) + bb[2 * e];
+                        const float v1 = __uint_as_float(r[8 * j + 2 * e + 1]) + bb[2 * e + 1];
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    const int chunk = p.c_chunk0 + part * 32 + chalf * 16 + c0 / 8 + j;
+                    *reinterpret_cast<uint4*>(cblk + (long long)chunk * CHUNK_BYTES) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            rs::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) rs::mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    rs::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) rs::tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -459,7 +594,16 @@ extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk
     p.bias = bias; p.n_blocks = (int)n_blocks; p.n_tiles = n_tiles; p.k_blocks = k_blocks;
     RS_REQUIRE(n_tiles * 128 <= NT_MAX_N, "rs_blk_gemm_nt: at most %d output columns", NT_MAX_N);
     const int grid = (int)(n_blocks < num_sms() ? n_blocks : num_sms());
-    if (k_blocks <= 4) {
+    static const bool wres_off = getenv("RS_NT_WRES") && atoi(getenv("RS_NT_WRES")) == 0;
+    if (k_blocks <= 4 && n_tiles % 2 == 0 && n_tiles / 2 <= 8 && n_blocks >= 2 * num_sms() && !wres_off) {
+        // weight-resident: one CTA per (group, 256-column W slice); groups walk the blocks together
+        const int n_parts = n_tiles / 2;
+        const int groups = num_sms() / n_parts;
+        const int smem = k_blocks * 2 * PIECE_BYTES + WRES_STAGES * PIECE_BYTES + 256 * 4 + 256;
+        RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_nt_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        blk_gemm_nt_wres_kernel<<<groups * n_parts, NT_THREADS, smem, stream>>>(p, n_parts);
+        rs::count_launch();
+    } else if (k_blocks <= 4) {
         const int smem = 2 * 4 * PIECE_BYTES + 5 * PIECE_BYTES + NT_MAX_N * 4 + 256;
         RS_CUDA_OK(cudaFuncSetAttribute(blk_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         blk_gemm_nt_kernel<true><<<grid, NT_THREADS, smem, stream>>>(p);

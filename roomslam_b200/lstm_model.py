@@ -11,6 +11,7 @@ element-wise ops.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -21,17 +22,73 @@ from . import _lib
 from .functional import _need_cuda, _p, _stream, colsum, ktime, linear_nt, matmul_nn, matmul_tn, padded
 
 
+
+# ---- fp32-accurate GEMMs on the bf16 tensor cores ("bf16x6", csrc/split_bf16.cu + csrc/gemm_tc.cu) -------------------
+# Operands are split into bf16 (hi, mid, lo) triples; the six significant partial products run as ONE tcgen05 GEMM over a
+# six times longer K (weight gradients: six accumulating passes over the thirds).  bf16 products are exact in the fp32
+# accumulator, so the result is fp32-grade -- at tensor-core instead of CUDA-core speed.  Used when the row count is
+# large enough to matter.
+TC_MIN_ROWS = 4096
+TC_ENABLED = os.environ.get("RS_LSTM_TC", "1") != "0"
+OUT_F32 = 4
+_HI, _MID, _LO = 5, 2, 0            # column sixths of an A-role buffer that hold hi, mid, lo
+
+
+def _kpad(cols: int) -> int:
+    return (cols + 127) // 128 * 128
+
+
+def split3(x2d: torch.Tensor, role_b: bool = False):
+    """fp32 [rows, cols] -> (bf16 [rows, 6*kpad], kpad) in the A-role or B-role layout of rs_split_bf16x6."""
+    x2d = x2d.float()
+    if x2d.stride(1) != 1:
+        x2d = x2d.contiguous()
+    rows, cols = x2d.shape
+    kp = _kpad(cols)
+    out = torch.empty(rows, 6 * kp, dtype=torch.bfloat16, device=x2d.device)
+    _lib.call("rs_split_bf16x6", _p(x2d), x2d.stride(0), rows, cols, kp, int(role_b), _p(out), 6 * kp, _stream(x2d))
+    return out, kp
+
+
+def nt_tc(a3: torch.Tensor, b3: torch.Tensor, bias, out: torch.Tensor):
+    """out[M, N] (fp32) = A . B^T + bias from split operands (a3: [M, 6kp] A role, b3: [N, 6kp] B role); N % 128 == 0."""
+    _lib.call("rs_gemm_bf16_nt", _p(a3), a3.stride(0), _p(b3), b3.stride(0), _p(out), out.stride(0), _p(bias), a3.shape[0],
+              b3.shape[0], a3.shape[1], OUT_F32, _stream(out))
+
+
+def tn_tc(a3, kpa, a_col0, m_out, b3, kpb, n_out, out, a_shift=0, b_shift=0):
+    """out[m_out, n_out] (fp32, zero-initialised by the caller) += A[:, a_col0:a_col0+m_out]^T . B[:, :n_out], row r + a_shift
+    of A paired with row r + b_shift of B; both operands in the A-role split layout."""
+    rows = a3.shape[0] - max(a_shift, b_shift)
+    for ta, tb in ((_LO, _HI), (_HI, _LO), (_MID, _MID), (_MID, _HI), (_HI, _MID), (_HI, _HI)):
+        _lib.call("rs_gemm_bf16_tn_acc", _p(a3), a3.stride(0), a3.shape[0], ta * kpa + a_col0, a_shift, _p(b3), b3.stride(0),
+                  b3.shape[0], tb * kpb, b_shift, _p(out), out.stride(0), m_out, n_out, rows, _stream(out))
+
+
+def _tc_ok(rows: int, *dims128) -> bool:
+    return TC_ENABLED and rows >= TC_MIN_ROWS and all(d % 128 == 0 for d in dims128)
+
+
 class LinearFn(torch.autograd.Function):
-    """y[M, N] = x[M, K] @ w[N, K]^T + b  on rs_sgemm (forward, dgrad, wgrad) and rs_colsum_f32 (bias gradient)."""
+    """y[M, N] = x[M, K] @ w[N, K]^T + b.  Large M: bf16x6 tensor-core GEMMs; otherwise rs_sgemm.  Bias gradient: rs_colsum_f32."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, allow_tc=False):
         _need_cuda(x, w, b)
         x, w = x.contiguous().float(), w.contiguous().float()
+        bias = b.contiguous().float() if b is not None else None
         y = torch.empty(x.shape[0], w.shape[0], device=x.device)
-        with ktime("sgemm_kernel(linear)", 2.0 * x.shape[0] * w.shape[0] * w.shape[1]):
-            linear_nt(x, w, b.contiguous().float() if b is not None else None, y)
-        ctx.save_for_backward(x, w)
+        ctx.tc = allow_tc and _tc_ok(x.shape[0], w.shape[0])
+        if ctx.tc:
+            x3, kp = split3(x)
+            with ktime("gemm_tc_kernel(linear bf16x6)", 12.0 * x.shape[0] * w.shape[0] * kp):
+                nt_tc(x3, split3(w, role_b=True)[0], bias, y)
+            ctx.kp = kp
+            ctx.save_for_backward(x3, w)
+        else:
+            with ktime("sgemm_kernel(linear)", 2.0 * x.shape[0] * w.shape[0] * w.shape[1]):
+                linear_nt(x, w, bias, y)
+            ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         return y
 
@@ -39,22 +96,40 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous().float()
+        N, K = w.shape
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            matmul_nn(dy, w, dx)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            matmul_tn(dy, x, dw)
+        if ctx.tc:
+            dy3, kpy = split3(dy)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(dy.shape[0], K, device=w.device)
+                if K % 128 == 0:
+                    with ktime("gemm_tc_kernel(linear bf16x6)", 12.0 * dy.shape[0] * K * kpy):
+                        nt_tc(dy3, split3(w.t(), role_b=True)[0], None, dx)
+                else:
+                    matmul_nn(dy, w, dx)
+            if ctx.needs_input_grad[1]:
+                full = torch.zeros(N, ctx.kp, device=w.device)
+                with ktime("gemm_tc_kernel(linear bf16x6)", 12.0 * dy.shape[0] * N * ctx.kp):
+                    tn_tc(dy3, kpy, 0, N, x, ctx.kp, ctx.kp, full)
+                dw = full[:, :K].contiguous()
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                matmul_nn(dy, w, dx)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty_like(w)
+                matmul_tn(dy, x, dw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(w.shape[0], device=w.device)
+            db = torch.empty(N, device=w.device)
             colsum(dy, db)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], allow_tc: bool = False) -> torch.Tensor:
+    """allow_tc: the per-token projections (millions of rows) may use the bf16x6 tensor-core GEMM; the per-query tail
+    ([B*Q, D] rows, ~1 % of the work) stays on the CUDA-core GEMM."""
     lead = x.shape[:-1]
-    return LinearFn.apply(x.reshape(-1, x.shape[-1]), w, b).view(*lead, w.shape[0])
+    return LinearFn.apply(x.reshape(-1, x.shape[-1]), w, b, allow_tc).view(*lead, w.shape[0])
 
 
 class LSTMLayerFn(torch.autograd.Function):
@@ -81,8 +156,14 @@ class LSTMLayerFn(torch.autograd.Function):
         w_hh_t = w_hh_cat.transpose(1, 2).contiguous()                            # [2, H, 4H]
         bias = (torch.cat([b_ih, b_ih_r], 0) + torch.cat([b_hh, b_hh_r], 0)).contiguous().float()
         P = torch.empty(B, Tp, 8 * H, device=dev)
-        with ktime("sgemm_kernel(lstm projection)", 2.0 * B * Tp * 8 * H * I):
-            linear_nt(xin.view(B * Tp, I), w_ih_cat, bias, P.view(B * Tp, 8 * H))
+        tc = _tc_ok(B * Tp, I, 2 * H)
+        if tc:
+            xin3, kpi = split3(xin.view(B * Tp, I))
+            with ktime("gemm_tc_kernel(lstm projection bf16x6)", 12.0 * B * Tp * 8 * H * kpi):
+                nt_tc(xin3, split3(w_ih_cat, role_b=True)[0], bias, P.view(B * Tp, 8 * H))
+        else:
+            with ktime("sgemm_kernel(lstm projection)", 2.0 * B * Tp * 8 * H * I):
+                linear_nt(xin.view(B * Tp, I), w_ih_cat, bias, P.view(B * Tp, 8 * H))
         out = padded(B, T, 2 * H, dev)
         saved = torch.empty(2, B, T, 5, H, device=dev) if need_grad else None
         with ktime("lstm_fwd_f32_kernel", 2.0 * B * T * 2 * 4 * H * H):
@@ -90,7 +171,8 @@ class LSTMLayerFn(torch.autograd.Function):
         del P
         ctx.dims = (B, T, I, H)
         ctx.mask = mask
-        ctx.save_for_backward(out, saved, xin, w_ih_cat, w_hh_cat)
+        ctx.tc = tc
+        ctx.save_for_backward(out, saved, xin3 if tc else xin, w_ih_cat, w_hh_cat)
         return out
 
     @staticmethod
@@ -106,20 +188,37 @@ class LSTMLayerFn(torch.autograd.Function):
         with ktime("lstm_bwd_f32_kernel", 2.0 * B * T * 2 * 4 * H * H):
             _lib.call("rs_lstm_bwd_f32", _p(d_out), 2 * H, Tp, 1, _p(saved), _p(w_hh_cat), _p(dG), 8 * H, Tp, 1, B, T, H, st)
         dG2, out2 = dG.view(M, 8 * H), out.view(M, 2 * H)
-        dW_ih = torch.empty(8 * H, I, device=dev)
-        with ktime("sgemm_kernel(lstm wgrad)", 2.0 * M * 8 * H * (I + H)):
-            matmul_tn(dG2, xin.view(M, I), dW_ih)
-            # h_{t-1} of a step is the row before (forward) / after (reverse); the zero pad rows close the boundary
-            dW_hh = torch.empty(2, 4 * H, H, device=dev)
-            matmul_tn(dG2[1:, 0:4 * H], out2[:M - 1, 0:H], dW_hh[0])
-            matmul_tn(dG2[:M - 1, 4 * H:8 * H], out2[1:, H:2 * H], dW_hh[1])
+        # h_{t-1} of a step is the row before (forward) / after (reverse); the zero pad rows close the boundary
+        if ctx.tc:
+            dG3, kpg = split3(dG2)
+            out3, kpo = split3(out2)
+            kpi = xin.shape[1] // 6
+            dW_ih = torch.zeros(8 * H, I, device=dev)
+            hh = torch.zeros(2, 4 * H, 2 * H, device=dev)
+            with ktime("gemm_tc_kernel(lstm wgrad bf16x6)", 12.0 * M * 8 * H * (I + 2 * H)):
+                tn_tc(dG3, kpg, 0, 8 * H, xin, kpi, I, dW_ih)
+                tn_tc(dG3, kpg, 0, 4 * H, out3, kpo, 2 * H, hh[0], a_shift=1, b_shift=0)
+                tn_tc(dG3, kpg, 4 * H, 4 * H, out3, kpo, 2 * H, hh[1], a_shift=0, b_shift=1)
+            dW_hh = torch.stack([hh[0, :, 0:H], hh[1, :, H:2 * H]], 0)
+            del out3
+        else:
+            dW_ih = torch.empty(8 * H, I, device=dev)
+            with ktime("sgemm_kernel(lstm wgrad)", 2.0 * M * 8 * H * (I + H)):
+                matmul_tn(dG2, xin.view(M, I), dW_ih)
+                dW_hh = torch.empty(2, 4 * H, H, device=dev)
+                matmul_tn(dG2[1:, 0:4 * H], out2[:M - 1, 0:H], dW_hh[0])
+                matmul_tn(dG2[:M - 1, 4 * H:8 * H], out2[1:, H:2 * H], dW_hh[1])
         db = torch.empty(8 * H, device=dev)
         colsum(dG2, db)
         d_xin = None
         if ctx.needs_input_grad[0]:
             d_xin = torch.empty(B, Tp, I, device=dev)
-            with ktime("sgemm_kernel(lstm dgrad)", 2.0 * M * 8 * H * I):
-                matmul_nn(dG2, w_ih_cat, d_xin.view(M, I))
+            if ctx.tc:
+                with ktime("gemm_tc_kernel(lstm dgrad bf16x6)", 12.0 * M * I * kpg):
+                    nt_tc(dG3, split3(w_ih_cat.t(), role_b=True)[0], None, d_xin.view(M, I))
+            else:
+                with ktime("sgemm_kernel(lstm dgrad)", 2.0 * M * 8 * H * I):
+                    matmul_nn(dG2, w_ih_cat, d_xin.view(M, I))
             if ctx.mask is not None:
                 m = ctx.mask.contiguous().float()
                 _lib.call("rs_seq_mul_f32", _p(d_xin), I, Tp, 1, _p(m), I, T, 0, _p(d_xin), I, Tp, 1, B, T, I, st)
@@ -221,7 +320,7 @@ class LSTMTraceEncoder(nn.Module):
         mean, rms, count = trace_stats(traces, mask_u8)
         xp = padded(B, N, Fdim, traces.device)
         xp[:, 1:N + 1] = traces
-        cur = linear(xp, self.input_proj.weight, self.input_proj.bias)
+        cur = linear(xp, self.input_proj.weight, self.input_proj.bias, allow_tc=True)
         for l in range(self.num_layers):
             m = None
             if l > 0:
@@ -232,7 +331,7 @@ class LSTMTraceEncoder(nn.Module):
                     m = torch.bernoulli(torch.full((B, N, self.d_model), keep, device=traces.device)) / keep
             w = [getattr(self.lstm, f"{n}_l{l}{sfx}") for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
             cur = LSTMLayerFn.apply(cur, m, *w)
-        memory = linear(cur, self.out_proj.weight, self.out_proj.bias)          # pad rows hold the bias; never read as tokens
+        memory = linear(cur, self.out_proj.weight, self.out_proj.bias, allow_tc=True)          # pad rows hold the bias; never read as tokens
         return memory, mean, rms, count
 
 

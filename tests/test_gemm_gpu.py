@@ -39,7 +39,10 @@ def test_gemm_bf16_tn_row_major(rows, M, N, sa, sb, ca, cb):
 
 @pytest.mark.parametrize("B,T,Ca,kcols,N,Cc,c0", [(128, 1, 64, [0], 128, 128, 0), (200, 5, 256, [0, 64, 128, 192], 768, 768, 0),
                                                     (300, 7, 1024, [0, 64, 128, 192, 256, 320, 512, 576, 640, 704, 768, 832], 256, 256, 0),
-                                                    (128, 3, 128, [64], 128, 512, 256)])
+                                                    (128, 3, 128, [64], 128, 512, 256),
+                                                    # >= 2 x 148 blocks and an even number of N tiles: the weight-resident variant
+                                                    (700, 60, 256, [0, 64, 128, 192], 768, 768, 0), (256, 149, 128, [0, 64], 256, 512, 128),
+                                                    (1300, 40, 256, [64, 128, 192], 512, 1024, 256)])
 def test_blk_gemm_nt_tile_major(B, T, Ca, kcols, N, Cc, c0):
     torch.manual_seed(2)
     x = torch.randn(B, T, Ca, device="cuda")
@@ -81,3 +84,29 @@ def test_blk_gemm_tn_tile_major_with_time_shift(shift):
         bb[:, :-1] = src[:, 1:]
     ref = 1.0 + torch.einsum("btm,btn->mn", aa, bb)
     assert float((C - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 512, 128), (4100, 128, 11), (9000, 128, 512)])
+def test_bf16x6_split_gemm_is_fp32_grade(M, N, K):
+    """rs_split_bf16x6 + rs_gemm_bf16_nt / rs_gemm_bf16_tn_acc against an fp64 matmul: error at the fp32 level."""
+    from roomslam_b200.lstm_model import nt_tc, split3, tn_tc
+    torch.manual_seed(M)
+    a = torch.randn(M, K, device="cuda") * torch.rand(M, 1, device="cuda") * 10
+    w = torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    a3, kp = split3(a)
+    out = torch.empty(M, N, device="cuda")
+    nt_tc(a3, split3(w, role_b=True)[0], bias, out)
+    ref = a.double() @ w.double().t() + bias.double()
+    # the tensor core truncates its fp32 accumulator at every K=16 step of the final (hi.hi) sixth: ~6e-8 x K/16
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+    # hi + mid + lo reproduces x to 24 bits
+    thirds = a3.view(M, 6, kp)[:, [0, 2, 5], :K].double().sum(1)            # lo, mid, hi sixths of the A role
+    assert float((thirds - a.double()).abs().max() / a.abs().max()) < 2e-7
+    # weight gradient: dW[N, K] = dY^T A with a one-row shift between the operands
+    dy = torch.randn(M, N, device="cuda")
+    dy3, kpy = split3(dy)
+    dw = torch.zeros(N, kp, device="cuda")
+    tn_tc(dy3, kpy, 0, N, a3, kp, kp, dw, a_shift=1, b_shift=0)
+    ref_w = dy[1:].double().t() @ a[:-1].double()
+    assert float((dw[:, :K].double() - ref_w).abs().max() / ref_w.abs().max()) < 5e-6

@@ -45,10 +45,13 @@ def test_against_reference_golden(name, tag):
             assert rel_err(g.flatten()[:32].cpu(), golden[f"{name}_{tag}_gradhead/{k}"]) < TOL, k
 
 
-@pytest.mark.parametrize("d_model,Q,B,N", [(64, 5, 1, 1), (64, 33, 2, 70), (128, 30, 5, 97), (256, 50, 2, 40), (128, 80, 300, 33)])
+@pytest.mark.parametrize("d_model,Q,B,N", [(64, 5, 1, 1), (64, 33, 2, 70), (128, 30, 5, 97), (256, 50, 2, 40), (128, 80, 36, 33), (128, 6, 300, 33)])
 def test_against_oracle_shapes(d_model, Q, B, N):
-    """Shapes the golden file does not hold: one token, > 32 queries (two query tiles), d_model 256 (streamed W_hh),
-    a batch large enough for the 4-traces-per-thread-row variant."""
+    """Shapes the golden file does not hold: one token, > 32 queries (two / three query tiles), d_model 256 (streamed W_hh),
+    a batch large enough for several traces per CTA and for the tensor-core (bf16x6) GEMM path (>= 4096 rows).
+    The large batch keeps the query count small: every [B*Q, 128] ReLU layer of the heads is a discontinuity, and with
+    millions of units ANY two fp32 evaluation orders (torch CPU vs fp64 included) put a few pre-activations on opposite
+    sides of zero, which moves the head weight gradients by ~2e-4 per flipped unit (tools/lstm_err_probe.py)."""
     # two oracles, fp32 and fp64: a ReLU pre-activation that rounds to the other side of 0 in fp64 moves a head gradient
     # by ~2e-4 for BOTH fp32 implementations (they then agree with each other), while torch's fp32 CPU sums over a
     # 300-trace batch can themselves be ~1e-3 off the fp64 value the kernels match to 2e-6 (tools/lstm_err_probe.py).
@@ -94,3 +97,31 @@ def test_state_dict_round_trip_with_oracle():
     ref = TraceToColliderLSTMRef(128, 30)
     ref.load_state_dict(m.state_dict(), strict=True)
     m.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_tensor_core_gemm_path_matches_fp64_oracle():
+    """Rows >= 4096 switch the time-parallel GEMMs to the bf16x6 tensor-core path; same 1e-4 bar, and it must agree with
+    the CUDA-core path on the same input."""
+    from roomslam_b200 import lstm_model
+    d_model, Q, B, N = 128, 30, 40, 200
+    ref64 = TraceToColliderLSTMRef(d_model, Q).eval().double()
+    ref64.load_state_dict({k: v.double() for k, v in seeded_state(TraceToColliderLSTMRef(d_model, Q), 5).items()})
+    model = gpu_model(d_model, Q, 5)
+    g = torch.Generator().manual_seed(3)
+    traces = torch.randn(B, N, 11, generator=g)
+    lengths = torch.randint(20, N + 1, (B,), generator=g)
+    mask = torch.arange(N)[None, :] < lengths[:, None]
+    traces = traces * mask[..., None]
+    wb, wc = torch.randn(B, Q, 6, generator=g), torch.randn(B, Q, 4, generator=g)
+    db, dc, _, dg = run(ref64, traces.double(), mask, wb.double(), wc.double())
+    results = {}
+    for flag in (True, False):
+        lstm_model.TC_ENABLED = flag
+        try:
+            results[flag] = run(model, traces.cuda(), mask.cuda(), wb.cuda(), wc.cuda())
+        finally:
+            lstm_model.TC_ENABLED = True
+    for flag, (gb, gc, _, gg) in results.items():
+        assert rel_err(gb.cpu(), db) < TOL and rel_err(gc.cpu(), dc) < TOL, flag
+        worst = max((rel_err(gg[k].cpu(), dg[k]), k) for k in dg)
+        assert worst[0] < TOL, (flag, worst)
