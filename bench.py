@@ -536,6 +536,11 @@ def main():
     ap.add_argument("--suite", default="headline", choices=["headline", "next"],
                     help="'next': one JSON line per SURVEY.md 8(f) row instead of the headline line (single GPU)")
     args = ap.parse_args()
+    # Native libraries write banners to file descriptor 1 (NCCL prints its version at the first communicator init).
+    # The contract is ONE JSON line on stdout: keep Python's stdout on the real descriptor and point fd 1 at stderr.
+    sys.stdout.flush()
+    sys.stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.suite == "next":
         return run_next_rows(args)
     if args.warmup < 3 and args.impl == "ours":
