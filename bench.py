@@ -500,6 +500,25 @@ def run_next_rows(args):
             eval_ref.nms_order(boxes[b], logits[b])
         eval_ref.mean_average_precision(boxes[:S], logits[:S], gt[:S], labels[:S], valid[:S])
     t_cpu = _time_cpu(cpu_eval)
+    # ---- BASELINE config 5: batched inference + IoU / mAP evaluation of the GRU model, 262144 traces x 500 steps ----
+    from roomslam_b200 import RoomSLAM, synth
+    from roomslam_b200.evaluation import SlotEvaluator
+    n5 = 262144
+    model5 = RoomSLAM(precision="bf16").cuda().eval()
+    x5, t5 = synth.make_sample(n5, SEQ_LEN, MAX_OBJECTS, seed=0, device="cuda")
+
+    def c5_step():
+        ev = SlotEvaluator(4, 0.5)
+        with torch.no_grad():
+            for s0 in range(0, n5, 16384):
+                ev.update(model5(x5[s0:s0 + 16384]), {k: v[s0:s0 + 16384] for k, v in t5.items()})
+        return ev.compute()
+    ms5 = _time_gpu(c5_step, max(1, args.steps // 2), 1)
+    print(json.dumps({"row": "BASELINE config 5: batched GRU inference + IoU / mAP evaluation (incl. the host read of the metrics)",
+                      "metric": "traces/s", "value": round(n5 / ms5 * 1e3, 0), "ms_per_step": round(ms5, 2), "dtype": "bf16",
+                      "config": {"workload": f"{n5} traces x {SEQ_LEN} steps, H 128, 2 layers, 10 slots; chunks of 16384"}}), flush=True)
+    del x5, t5, model5
+
     print(json.dumps({"row": "8(f)4 evaluation: matched metrics + NMS + mAP (incl. the host read of the results)",
                       "metric": "scenes/s", "value": round(B / ms * 1e3, 0), "ms_per_step": round(ms, 3), "dtype": "f32",
                       "config": {"workload": f"{B} scenes x {Q} queries x {M} collider slots"},

@@ -2,7 +2,8 @@
 """Thin equivalent of the upstream README's evaluate.py (README.md:76-80; absent upstream).
 
     python evaluate.py --checkpoint checkpoints/best_model.pth --data_dir data/sample --compare_baseline
-Reports the loss terms, class accuracy and axis-aligned IoU over the valid slots (fixed slot assignment, decision D8)
+Reports the loss terms, class / validity accuracy, axis-aligned IoU over the valid slots, detection precision / recall and
+mAP@0.5 (fixed slot assignment, decision D8; roomslam_b200.evaluation.SlotEvaluator)
 and, with --compare_baseline, the occupancy / stationary summary of the rule-based baseline."""
 import argparse
 import json
@@ -10,14 +11,7 @@ import json
 import torch
 
 from roomslam_b200 import OccupancyHeatmapBaseline, RoomSLAM, data
-
-
-def box_iou(p_pos, p_size, t_pos, t_size):
-    lo = torch.maximum(p_pos - p_size / 2, t_pos - t_size / 2)
-    hi = torch.minimum(p_pos + p_size / 2, t_pos + t_size / 2)
-    inter = (hi - lo).clamp_min(0).prod(-1)
-    union = p_size.prod(-1) + t_size.prod(-1) - inter
-    return inter / union.clamp_min(1e-9)
+from roomslam_b200.evaluation import SlotEvaluator
 
 
 def main():
@@ -34,11 +28,10 @@ def main():
     with torch.no_grad():
         pred = model(x.cuda())
         loss = model.compute_loss(pred, tg)
-    valid = tg["valid"] > 0
-    acc = ((pred["class_logits"].argmax(-1) == tg["classes"]) & valid).sum() / valid.sum().clamp_min(1)
-    iou = (box_iou(pred["positions"], pred["sizes"], tg["positions"], tg["sizes"]) * valid).sum() / valid.sum().clamp_min(1)
+    ev = SlotEvaluator(num_classes=pred["class_logits"].shape[-1], iou_thresh=0.5)
+    ev.update(pred, tg)
     report = {k: float(v) for k, v in loss.items()}
-    report.update(class_accuracy=float(acc), mean_iou=float(iou), n_traces=len(x))
+    report.update(ev.compute(), n_traces=len(x))
     if args.compare_baseline:
         b = OccupancyHeatmapBaseline()
         occ, stat, dropped = b.bin(x.cuda())

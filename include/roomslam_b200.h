@@ -233,6 +233,15 @@ int rs_ap_flags(const float* pred_boxes, const float* pred_logits, const float* 
                 const unsigned char* gt_valid, int B, int Q, int M, float iou_thr, int* flags, float* conf, int* label, int* n_gt,
                 void* stream);
 
+/* Evaluation of the README GRU model's slot outputs (README.md:93-132; BASELINE config 5), n_slots = B * max_objects:
+ * 2-D axis-aligned IoU per slot, predicted class, conf = sigmoid(validity) * max class probability, flag = target slot
+ * valid && class right && IoU >= iou_thr, n_gt[C] += valid target slots per class; counts[6] (double, device) +=
+ * [IoU sum over valid slots, valid slots, class hits, validity hits, TP, predicted-valid].  workspace: 6 * 1184 doubles. */
+int rs_slot_eval(const float* class_logits, const float* positions, const float* sizes, const float* validity_logits,
+                 const int64_t* t_classes, const float* t_positions, const float* t_sizes, const float* t_valid,
+                 int64_t n_slots, int C, float iou_thr, float* conf, int* label, int* flag, int* n_gt, double* workspace,
+                 double* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,3 +127,26 @@ def mean_average_precision(boxes, logits, gt_boxes, gt_labels, gt_valid, iou_thr
     aps = [average_precision(conf[label == c], flags[label == c], int(n_gt[c])) for c in range(4)]
     valid = [a for a in aps if not np.isnan(a)]
     return (float(np.mean(valid)) if valid else 0.0), aps
+
+
+def slot_eval(pred, target, iou_thr=0.5):
+    """Evaluation of the README GRU model's slot outputs (spec only, README.md:93-132: PARITY UNPINNED): the torch-CPU
+    definition of what roomslam_b200.evaluation.SlotEvaluator computes."""
+    cl, pos, size, vl = pred["class_logits"], pred["positions"], pred["sizes"], pred["validity_logits"]
+    tv = target["valid"] > 0.5
+    label = cl.argmax(-1)
+    conf = torch.sigmoid(vl) * torch.softmax(cl, -1).max(-1).values
+    lo = torch.maximum(pos - size / 2, target["positions"] - target["sizes"] / 2)
+    hi = torch.minimum(pos + size / 2, target["positions"] + target["sizes"] / 2)
+    inter = (hi - lo).clamp_min(0).prod(-1)
+    iou = inter / (size.prod(-1) + target["sizes"].prod(-1) - inter).clamp_min(1e-9)
+    flag = tv & (label == target["classes"]) & (iou >= iou_thr)
+    pv = torch.sigmoid(vl) > 0.5
+    C = cl.shape[-1]
+    n_gt = np.array([int((tv & (target["classes"] == c)).sum()) for c in range(C)])
+    aps = [average_precision(conf[label == c].numpy(), flag[label == c].numpy().astype(np.float64), int(n_gt[c])) for c in range(C)]
+    ok = [a for a in aps if not np.isnan(a)]
+    nv = max(int(tv.sum()), 1)
+    return {"mean_iou": float(iou[tv].sum()) / nv, "class_accuracy": float((label == target["classes"])[tv].sum()) / nv,
+            "validity_accuracy": float((pv == tv).float().mean()), "precision": float(flag.sum()) / max(int(pv.sum()), 1),
+            "recall": float(flag.sum()) / nv, "mAP": float(np.mean(ok)) if ok else 0.0, "AP_per_class": aps}

@@ -186,6 +186,67 @@ ap_flags_kernel(const float* __restrict__ pred_boxes, const float* __restrict__ 
     }
 }
 
+
+// ---- evaluation of the README GRU model (fixed object slots + validity head, README.md:93-132; BASELINE config 5) ----
+// One thread per (trace, slot): 2-D axis-aligned IoU (orientation ignored, as in all shipped IoU code), predicted class,
+// confidence = sigmoid(validity logit) * max class probability, true-positive flag (target slot valid, class right,
+// IoU >= thr); block partials of [IoU sum over valid slots, valid slots, class hits, validity hits, TP, predicted valid].
+__global__ void __launch_bounds__(256)
+slot_eval_kernel(const float* __restrict__ cls, const float* __restrict__ pos, const float* __restrict__ size,
+                 const float* __restrict__ vlogit, const long long* __restrict__ t_cls, const float* __restrict__ t_pos,
+                 const float* __restrict__ t_size, const float* __restrict__ t_valid, long long total, int C, float iou_thr,
+                 float* __restrict__ conf, int* __restrict__ label, int* __restrict__ flag, int* __restrict__ n_gt,
+                 double* __restrict__ partial) {
+    __shared__ double red[6][8];
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const float* l = cls + e * C;
+        int best = 0;
+        for (int c = 1; c < C; ++c) if (l[c] > l[best]) best = c;
+        float den = 0.0f;
+        for (int c = 0; c < C; ++c) den += expf(l[c] - l[best]);
+        const float pv = 1.0f / (1.0f + expf(-vlogit[e]));
+        float inter = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float lo = fmaxf(pos[e * 2 + k] - size[e * 2 + k] / 2, t_pos[e * 2 + k] - t_size[e * 2 + k] / 2);
+            const float hi = fminf(pos[e * 2 + k] + size[e * 2 + k] / 2, t_pos[e * 2 + k] + t_size[e * 2 + k] / 2);
+            inter = inter * fmaxf(hi - lo, 0.0f);
+        }
+        const float uni = (size[e * 2] * size[e * 2 + 1] + t_size[e * 2] * t_size[e * 2 + 1]) - inter;
+        const float iou = inter / fmaxf(uni, 1e-9f);
+        const bool tv = t_valid[e] > 0.5f;
+        const int tc = (int)t_cls[e];
+        const bool hit = tv && best == tc && iou >= iou_thr;
+        conf[e] = pv / den;
+        label[e] = best;
+        flag[e] = hit ? 1 : 0;
+        if (tv) { atomicAdd(&n_gt[tc], 1); s[0] += iou; s[1] += 1.0; s[2] += (best == tc) ? 1.0 : 0.0; }
+        s[3] += ((pv > 0.5f) == tv) ? 1.0 : 0.0;
+        s[4] += hit ? 1.0 : 0.0;
+        s[5] += (pv > 0.5f) ? 1.0 : 0.0;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = 0; k < 6; ++k) {
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        if (lane == 0) red[k][warp] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        partial[(long long)blockIdx.x * 6 + threadIdx.x] = t;
+    }
+}
+
+__global__ void slot_eval_accumulate_kernel(const double* __restrict__ partial, int n, double* __restrict__ counts) {
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int b = 0; b < n; ++b) t += partial[(long long)b * 6 + threadIdx.x];
+        counts[threadIdx.x] += t;
+    }
+}
+
 }  // namespace
 
 extern "C" int rs_eval_pairs(const float* pred_boxes, const float* pred_logits, const float* gt_boxes, const int64_t* gt_labels,
@@ -228,6 +289,28 @@ extern "C" int rs_ap_flags(const float* pred_boxes, const float* pred_logits, co
     if (B == 0) return 0;
     ap_flags_kernel<<<B, 32, 0, stream>>>(pred_boxes, pred_logits, gt_boxes, reinterpret_cast<const long long*>(gt_labels), gt_valid, Q,
                                           M, iou_thr, flags, conf, label, n_gt);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_slot_eval(const float* class_logits, const float* positions, const float* sizes, const float* validity_logits,
+                            const int64_t* t_classes, const float* t_positions, const float* t_sizes, const float* t_valid,
+                            int64_t n_slots, int C, float iou_thr, float* conf, int* label, int* flag, int* n_gt,
+                            double* workspace, double* counts, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(class_logits && positions && sizes && validity_logits && t_classes && t_positions && t_sizes && t_valid && conf &&
+                   label && flag && n_gt && workspace && counts, "rs_slot_eval: null pointer");
+    RS_REQUIRE(C >= 1 && C <= 64 && n_slots >= 0, "rs_slot_eval: bad sizes");
+    if (n_slots == 0) return 0;
+    long long blocks = (n_slots + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    slot_eval_kernel<<<(int)blocks, 256, 0, stream>>>(class_logits, positions, sizes, validity_logits,
+                                                      reinterpret_cast<const long long*>(t_classes), t_positions, t_sizes, t_valid,
+                                                      n_slots, C, iou_thr, conf, label, flag, n_gt, workspace);
+    rs::count_launch();
+    slot_eval_accumulate_kernel<<<1, 32, 0, stream>>>(workspace, (int)blocks, counts);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

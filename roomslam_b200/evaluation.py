@@ -100,13 +100,12 @@ def ap_flags(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_thresh: float = 
     return conf, label, flags, n_gt
 
 
-def mean_average_precision(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_thresh: float = 0.5) -> Tuple[float, List[float]]:
-    """mAP@iou_thresh over the 4 collider classes (all-point interpolated AP, classes without colliders skipped).
-    The per-scene claiming runs in rs_ap_flags; the dataset-wide ranking is one device sort + prefix sums."""
-    conf, label, flags, n_gt = ap_flags(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_thresh)
+def _average_precisions(conf, label, flags, n_gt) -> Tuple[float, List[float]]:
+    """All-point interpolated AP per class from (confidence, predicted class, TP flag) of every prediction and the
+    number of ground-truth objects per class; one device sort + prefix sums per class."""
     conf, label, flags = conf.flatten().double(), label.flatten(), flags.flatten().double()
     aps: List[float] = []
-    for c in range(4):
+    for c in range(n_gt.numel()):
         total = int(n_gt[c])
         if total == 0:
             aps.append(float("nan"))
@@ -124,3 +123,47 @@ def mean_average_precision(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_th
         aps.append(float(((rec[1:] - rec[:-1]) * prec[1:]).sum()))
     valid = [a for a in aps if a == a]
     return (sum(valid) / len(valid) if valid else 0.0), aps
+
+
+def mean_average_precision(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_thresh: float = 0.5) -> Tuple[float, List[float]]:
+    """mAP@iou_thresh over the 4 collider classes (all-point interpolated AP, classes without colliders skipped).
+    The per-scene claiming runs in rs_ap_flags; the dataset-wide ranking is one device sort + prefix sums."""
+    return _average_precisions(*ap_flags(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_thresh))
+
+
+class SlotEvaluator:
+    """Evaluation of the README GRU model (``RoomSLAM``: fixed object slots + validity head, README.md:93-132) at
+    BASELINE config-5 scale: ``update(pred, target)`` per chunk of traces (no host sync), ``compute()`` once.
+    Metrics: mean IoU and class accuracy over the valid target slots, validity accuracy over all slots, precision /
+    recall of (valid, class right, IoU >= thr) detections, and mAP@thr ranked by sigmoid(validity) * class probability."""
+
+    def __init__(self, num_classes: int = 4, iou_thresh: float = 0.5, device="cuda"):
+        self.C, self.thr = num_classes, float(iou_thresh)
+        self.counts = torch.zeros(6, dtype=torch.float64, device=device)
+        self.n_gt = torch.zeros(num_classes, dtype=torch.int32, device=device)
+        self.n_slots = 0
+        self._conf, self._label, self._flag = [], [], []
+
+    def update(self, pred: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> None:
+        cl = pred["class_logits"].detach().contiguous().float()
+        B, N, C = cl.shape
+        args = [cl, pred["positions"].detach().contiguous().float(), pred["sizes"].detach().contiguous().float(),
+                pred["validity_logits"].detach().contiguous().float(), target["classes"].contiguous().long(),
+                target["positions"].contiguous().float(), target["sizes"].contiguous().float(), target["valid"].contiguous().float()]
+        _need_cuda(*args)
+        dev = cl.device
+        conf = torch.empty(B, N, device=dev)
+        label = torch.empty(B, N, dtype=torch.int32, device=dev)
+        flag = torch.empty(B, N, dtype=torch.int32, device=dev)
+        ws = torch.empty(6 * 1184, dtype=torch.float64, device=dev)
+        _lib.call("rs_slot_eval", *[_p(a) for a in args], B * N, C, self.thr, _p(conf), _p(label), _p(flag), _p(self.n_gt), _p(ws),
+                  _p(self.counts), _stream(cl))
+        self._conf.append(conf); self._label.append(label); self._flag.append(flag)
+        self.n_slots += B * N
+
+    def compute(self) -> Dict[str, float]:
+        iou_sum, n_valid, cls_hits, val_hits, tp, n_pred = self.counts.cpu().tolist()
+        mAP, aps = _average_precisions(torch.cat(self._conf), torch.cat(self._label), torch.cat(self._flag), self.n_gt)
+        return {"mean_iou": iou_sum / max(n_valid, 1.0), "class_accuracy": cls_hits / max(n_valid, 1.0),
+                "validity_accuracy": val_hits / max(self.n_slots, 1), "precision": tp / max(n_pred, 1.0),
+                "recall": tp / max(n_valid, 1.0), "mAP": mAP, "AP_per_class": aps, "n_slots": self.n_slots}

@@ -93,3 +93,28 @@ def test_large_batch_counts_against_oracle():
         assert m[k] == want[k], k
     for k in ("mIoU", "cls_acc", "f1"):
         assert abs(m[k] - want[k]) < 1e-6, k
+
+
+def test_slot_evaluator_against_oracle_c5_style():
+    """BASELINE config 5 in miniature: chunked inference of the GRU model + slot evaluation, against the torch oracle."""
+    from roomslam_b200 import RoomSLAM, synth
+    from roomslam_b200.evaluation import SlotEvaluator
+    torch.manual_seed(0)
+    model = RoomSLAM(precision="bf16").cuda().eval()
+    x, tgt = synth.make_sample(3000, 500, 10, seed=4, device="cuda")
+    ev = SlotEvaluator(4, 0.5)
+    preds = []
+    with torch.no_grad():
+        for s in range(0, 3000, 1024):
+            pred = model(x[s:s + 1024])
+            # make the problem non-trivial: pull half of the predictions onto their targets
+            pred["positions"] = torch.where(torch.rand_like(pred["positions"]) < 0.5, tgt["positions"][s:s + 1024], pred["positions"])
+            pred["sizes"] = torch.where(torch.rand_like(pred["sizes"]) < 0.7, tgt["sizes"][s:s + 1024] * 1.05, pred["sizes"])
+            ev.update(pred, {k: v[s:s + 1024] for k, v in tgt.items()})
+            preds.append({k: v.float().cpu() for k, v in pred.items()})
+    got = ev.compute()
+    cat = {k: torch.cat([p[k] for p in preds]) for k in preds[0]}
+    want = eval_ref.slot_eval(cat, {k: v.cpu() for k, v in tgt.items()})
+    assert got["n_slots"] == 30000
+    for k in ("mean_iou", "class_accuracy", "validity_accuracy", "precision", "recall", "mAP"):
+        assert got[k] == pytest.approx(want[k], abs=2e-6), k
