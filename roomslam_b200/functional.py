@@ -12,6 +12,7 @@ ONE time-parallel GEMM with a one-row pointer shift.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -109,6 +110,53 @@ def colsum(a2d: torch.Tensor, out: torch.Tensor, accumulate=False):
     _lib.call("rs_colsum_f32", _p(a2d), a2d.stride(0), a2d.shape[0], a2d.shape[1], _p(out), int(accumulate), _stream(out))
 
 
+# ---- fp32-accurate GEMMs on the bf16 tensor cores ("bf16x6", csrc/split_bf16.cu + csrc/gemm_tc.cu) -------------------
+# Operands are split into bf16 (hi, mid, lo) triples; the six significant partial products run as ONE tcgen05 GEMM over a
+# six times longer K (weight gradients: six accumulating passes over the thirds).  bf16 products are exact in the fp32
+# accumulator, so the result is fp32-grade -- at tensor-core instead of CUDA-core speed.  Used when the row count is
+# large enough to matter.
+TC_MIN_ROWS = 4096
+TC_ENABLED = os.environ.get("RS_TC_GEMM", "1") != "0"
+OUT_F32 = 4
+_HI, _MID, _LO = 5, 2, 0            # column sixths of an A-role buffer that hold hi, mid, lo
+
+
+def _kpad(cols: int) -> int:
+    return (cols + 127) // 128 * 128
+
+
+def split3(x2d: torch.Tensor, role_b: bool = False):
+    """fp32 [rows, cols] -> (bf16 [rows, 6*kpad], kpad) in the A-role or B-role layout of rs_split_bf16x6."""
+    x2d = x2d.float()
+    if x2d.stride(1) != 1:
+        x2d = x2d.contiguous()
+    rows, cols = x2d.shape
+    kp = _kpad(cols)
+    out = torch.empty(rows, 6 * kp, dtype=torch.bfloat16, device=x2d.device)
+    _lib.call("rs_split_bf16x6", _p(x2d), x2d.stride(0), rows, cols, kp, int(role_b), _p(out), 6 * kp, _stream(x2d))
+    return out, kp
+
+
+def nt_tc(a3: torch.Tensor, b3: torch.Tensor, bias, out: torch.Tensor):
+    """out[M, N] (fp32) = A . B^T + bias from split operands (a3: [M, 6kp] A role, b3: [N, 6kp] B role); N % 128 == 0."""
+    _lib.call("rs_gemm_bf16_nt", _p(a3), a3.stride(0), _p(b3), b3.stride(0), _p(out), out.stride(0), _p(bias), a3.shape[0],
+              b3.shape[0], a3.shape[1], OUT_F32, _stream(out))
+
+
+def tn_tc(a3, kpa, a_col0, m_out, b3, kpb, n_out, out, a_shift=0, b_shift=0):
+    """out[m_out, n_out] (fp32, zero-initialised by the caller) += A[:, a_col0:a_col0+m_out]^T . B[:, :n_out], row r + a_shift
+    of A paired with row r + b_shift of B; both operands in the A-role split layout."""
+    rows = a3.shape[0] - max(a_shift, b_shift)
+    for ta, tb in ((_LO, _HI), (_HI, _LO), (_MID, _MID), (_MID, _HI), (_HI, _MID), (_HI, _HI)):
+        _lib.call("rs_gemm_bf16_tn_acc", _p(a3), a3.stride(0), a3.shape[0], ta * kpa + a_col0, a_shift, _p(b3), b3.stride(0),
+                  b3.shape[0], tb * kpb, b_shift, _p(out), out.stride(0), m_out, n_out, rows, _stream(out))
+
+
+def _tc_ok(rows: int, *dims128) -> bool:
+    return TC_ENABLED and rows >= TC_MIN_ROWS and all(d % 128 == 0 for d in dims128)
+
+
+
 def padded(B: int, T: int, C: int, device, dtype=torch.float32) -> torch.Tensor:
     buf = torch.empty(B, T + 2, C, device=device, dtype=dtype)
     buf[:, 0].zero_()
@@ -165,8 +213,15 @@ class GRULayerFn(torch.autograd.Function):
                 xp[:, 1:T + 1] = xin
                 xin, padded_in = xp, True
             P = torch.empty(B, T + 2, 6 * H, device=dev)
-            with ktime("sgemm_kernel(projection)", 2.0 * B * (T + 2) * 6 * H * Il):
-                linear_nt(xin.view(B * (T + 2), Il), w_ih_cat, b_ih_cat, P.view(B * (T + 2), 6 * H))
+            tc = _tc_ok(B * (T + 2), Il, H)
+            if tc:      # fp32-grade GEMM on the bf16 tensor cores (split operands, see csrc/split_bf16.cu)
+                xin3, kpi = split3(xin.view(B * (T + 2), Il))
+                with ktime("gemm_tc_kernel(projection bf16x6)", 12.0 * B * (T + 2) * 6 * H * kpi):
+                    nt_tc(xin3, split3(w_ih_cat, role_b=True)[0], b_ih_cat, P.view(B * (T + 2), 6 * H))
+                del xin3
+            else:
+                with ktime("sgemm_kernel(projection)", 2.0 * B * (T + 2) * 6 * H * Il):
+                    linear_nt(xin.view(B * (T + 2), Il), w_ih_cat, b_ih_cat, P.view(B * (T + 2), 6 * H))
             with ktime("gru_fwd_f32_kernel", rec_flops):
                 _lib.call("rs_gru_fwd_f32", 0, 0, 0, 0, Il, 0, _p(b_ih_cat), _p(P), 6 * H, T + 2, 1, _p(w_hh_t),
                           _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n), _p(gates), B, T, H, st)
@@ -200,24 +255,51 @@ class GRULayerFn(torch.autograd.Function):
             xp = padded(B, T, Il, dev)
             xp[:, 1:T + 1] = xin
             xin = xp
-        dW_ih = torch.empty(6 * H, Il, device=dev)
-        with ktime("sgemm_kernel(wgrad)", 2.0 * M * 6 * H * Il):
-            matmul_tn(dGx2, xin.view(M, Il), dW_ih)      # both directions at once
         db_ih = torch.empty(6 * H, device=dev)
         colsum(dGx2, db_ih)
         db_hh = torch.empty(6 * H, device=dev)
         colsum(dGh2, db_hh)
         # hidden-side weight gradients: pair row r of dGh with row r-1 (forward) / r+1 (reverse) of out;
         # the zero pad rows make the boundary steps (h_prev = 0) come out right
-        dW_hh = torch.empty(2, 3 * H, H, device=dev)
-        with ktime("sgemm_kernel(wgrad)", 2.0 * M * 6 * H * H):
-            matmul_tn(dGh2[1:, 0:3 * H], out2[:M - 1, 0:H], dW_hh[0])
-            matmul_tn(dGh2[:M - 1, 3 * H:6 * H], out2[1:, H:2 * H], dW_hh[1])
-        d_xin = None
+        tc_hh = _tc_ok(M, H)                    # hidden-side GEMM shapes: 3H x 2H per direction
+        tc_ih = tc_hh and Il % 128 == 0         # input-side: 6H x Il (layer 0 has Il = 2: CUDA cores)
+        d_xin = dX = None
         if ctx.needs_input_grad[0]:
             dX = torch.empty(B, Tp, Il, device=dev)
-            with ktime("sgemm_kernel(dgrad)", 2.0 * M * 6 * H * Il):
-                matmul_nn(dGx2, w_ih_cat, dX.view(M, Il))    # pad rows of dGx are zero -> pad rows of dX are zero
+        # fp32-grade GEMMs on the bf16 tensor cores where the shapes allow; the split copies are transient, one at a time
+        if tc_ih:
+            dGx3, kpg = split3(dGx2)
+            x3, kpi = split3(xin.view(M, Il))
+            dW_ih = torch.zeros(6 * H, Il, device=dev)
+            with ktime("gemm_tc_kernel(wgrad bf16x6)", 12.0 * M * 6 * H * Il):
+                tn_tc(dGx3, kpg, 0, 6 * H, x3, kpi, Il, dW_ih)
+            del x3
+            if dX is not None:
+                with ktime("gemm_tc_kernel(dgrad bf16x6)", 12.0 * M * Il * kpg):
+                    nt_tc(dGx3, split3(w_ih_cat.t(), role_b=True)[0], None, dX.view(M, Il))
+            del dGx3
+        else:
+            dW_ih = torch.empty(6 * H, Il, device=dev)
+            with ktime("sgemm_kernel(wgrad)", 2.0 * M * 6 * H * Il):
+                matmul_tn(dGx2, xin.view(M, Il), dW_ih)      # both directions at once
+            if dX is not None:
+                with ktime("sgemm_kernel(dgrad)", 2.0 * M * 6 * H * Il):
+                    matmul_nn(dGx2, w_ih_cat, dX.view(M, Il))    # pad rows of dGx are zero -> pad rows of dX are zero
+        if tc_hh:
+            dGh3, kph = split3(dGh2)
+            out3, kpo = split3(out2)
+            hh = torch.zeros(2, 3 * H, 2 * H, device=dev)
+            with ktime("gemm_tc_kernel(wgrad bf16x6)", 12.0 * M * 6 * H * 2 * H):
+                tn_tc(dGh3, kph, 0, 3 * H, out3, kpo, 2 * H, hh[0], a_shift=1, b_shift=0)
+                tn_tc(dGh3, kph, 3 * H, 3 * H, out3, kpo, 2 * H, hh[1], a_shift=0, b_shift=1)
+            dW_hh = torch.stack([hh[0, :, 0:H], hh[1, :, H:2 * H]], 0)
+            del dGh3, out3
+        else:
+            dW_hh = torch.empty(2, 3 * H, H, device=dev)
+            with ktime("sgemm_kernel(wgrad)", 2.0 * M * 6 * H * H):
+                matmul_tn(dGh2[1:, 0:3 * H], out2[:M - 1, 0:H], dW_hh[0])
+                matmul_tn(dGh2[:M - 1, 3 * H:6 * H], out2[1:, H:2 * H], dW_hh[1])
+        if dX is not None:
             if ctx.mask is not None:
                 m = ctx.mask.contiguous().float()
                 _lib.call("rs_seq_mul_f32", _p(dX), Il, Tp, 1, _p(m), Il, T, 0, _p(dX), Il, Tp, 1, B, T, Il, st)

@@ -11,7 +11,6 @@ element-wise ops.
 from __future__ import annotations
 
 import math
-import os
 from typing import Dict, Optional
 
 import torch
@@ -19,54 +18,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .functional import _need_cuda, _p, _stream, colsum, ktime, linear_nt, matmul_nn, matmul_tn, padded
+from . import functional as _F
+from .functional import (_need_cuda, _p, _stream, _tc_ok, colsum, ktime, linear_nt, matmul_nn, matmul_tn, nt_tc, padded, split3,
+                         tn_tc)
 
-
-
-# ---- fp32-accurate GEMMs on the bf16 tensor cores ("bf16x6", csrc/split_bf16.cu + csrc/gemm_tc.cu) -------------------
-# Operands are split into bf16 (hi, mid, lo) triples; the six significant partial products run as ONE tcgen05 GEMM over a
-# six times longer K (weight gradients: six accumulating passes over the thirds).  bf16 products are exact in the fp32
-# accumulator, so the result is fp32-grade -- at tensor-core instead of CUDA-core speed.  Used when the row count is
-# large enough to matter.
-TC_MIN_ROWS = 4096
-TC_ENABLED = os.environ.get("RS_LSTM_TC", "1") != "0"
-OUT_F32 = 4
-_HI, _MID, _LO = 5, 2, 0            # column sixths of an A-role buffer that hold hi, mid, lo
-
-
-def _kpad(cols: int) -> int:
-    return (cols + 127) // 128 * 128
-
-
-def split3(x2d: torch.Tensor, role_b: bool = False):
-    """fp32 [rows, cols] -> (bf16 [rows, 6*kpad], kpad) in the A-role or B-role layout of rs_split_bf16x6."""
-    x2d = x2d.float()
-    if x2d.stride(1) != 1:
-        x2d = x2d.contiguous()
-    rows, cols = x2d.shape
-    kp = _kpad(cols)
-    out = torch.empty(rows, 6 * kp, dtype=torch.bfloat16, device=x2d.device)
-    _lib.call("rs_split_bf16x6", _p(x2d), x2d.stride(0), rows, cols, kp, int(role_b), _p(out), 6 * kp, _stream(x2d))
-    return out, kp
-
-
-def nt_tc(a3: torch.Tensor, b3: torch.Tensor, bias, out: torch.Tensor):
-    """out[M, N] (fp32) = A . B^T + bias from split operands (a3: [M, 6kp] A role, b3: [N, 6kp] B role); N % 128 == 0."""
-    _lib.call("rs_gemm_bf16_nt", _p(a3), a3.stride(0), _p(b3), b3.stride(0), _p(out), out.stride(0), _p(bias), a3.shape[0],
-              b3.shape[0], a3.shape[1], OUT_F32, _stream(out))
-
-
-def tn_tc(a3, kpa, a_col0, m_out, b3, kpb, n_out, out, a_shift=0, b_shift=0):
-    """out[m_out, n_out] (fp32, zero-initialised by the caller) += A[:, a_col0:a_col0+m_out]^T . B[:, :n_out], row r + a_shift
-    of A paired with row r + b_shift of B; both operands in the A-role split layout."""
-    rows = a3.shape[0] - max(a_shift, b_shift)
-    for ta, tb in ((_LO, _HI), (_HI, _LO), (_MID, _MID), (_MID, _HI), (_HI, _MID), (_HI, _HI)):
-        _lib.call("rs_gemm_bf16_tn_acc", _p(a3), a3.stride(0), a3.shape[0], ta * kpa + a_col0, a_shift, _p(b3), b3.stride(0),
-                  b3.shape[0], tb * kpb, b_shift, _p(out), out.stride(0), m_out, n_out, rows, _stream(out))
-
-
-def _tc_ok(rows: int, *dims128) -> bool:
-    return TC_ENABLED and rows >= TC_MIN_ROWS and all(d % 128 == 0 for d in dims128)
 
 
 class LinearFn(torch.autograd.Function):

@@ -127,3 +127,33 @@ def test_state_dict_interchange_and_errors():
         dev(torch.zeros(2, 5, 3, device="cuda"))
     with pytest.raises(RuntimeError):
         dev(torch.zeros(2, 5, 2))      # CPU tensor: no fallback
+
+
+def test_fp32_mode_tensor_core_gemms_keep_parity():
+    """From 4096 rows (and H a multiple of 128) the fp32 mode's time-parallel GEMMs run as split-operand (bf16x6)
+    tensor-core GEMMs; the result must stay inside the same 1e-4 bar and agree with the CUDA-core path."""
+    import torch
+    from oracle.room_slam_ref import RoomSLAM as Ref
+    from roomslam_b200 import RoomSLAM, functional as Fn, synth
+    torch.manual_seed(3)
+    ref = Ref(hidden_size=128, dropout=0.0).double()
+    model = RoomSLAM(hidden_size=128, dropout=0.0, precision="fp32")
+    model.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    model = model.cuda()
+    x, tgt = synth.make_sample(48, 100, 10, seed=2)                       # 48 x 102 = 4896 rows
+    pr = ref(x.double()); lr = ref.compute_loss(pr, {k: (v.double() if v.is_floating_point() else v) for k, v in tgt.items()})
+    lr["total"].backward()
+    want = {k: p.grad.clone() for k, p in ref.named_parameters()}
+    xc, tc = x.cuda(), {k: v.cuda() for k, v in tgt.items()}
+    for flag in (True, False):
+        Fn.TC_ENABLED = flag
+        try:
+            model.zero_grad()
+            loss = model.compute_loss(model(xc), tc)
+            loss["total"].backward()
+        finally:
+            Fn.TC_ENABLED = True
+        assert abs(float(loss["total"]) - float(lr["total"])) < 1e-4 * abs(float(lr["total"]))
+        for k, p in model.named_parameters():
+            err = float((p.grad.double().cpu() - want[k]).abs().max() / max(1.0, float(want[k].abs().max())))
+            assert err < 1e-4, (flag, k, err)

@@ -102,7 +102,7 @@ def test_state_dict_round_trip_with_oracle():
 def test_tensor_core_gemm_path_matches_fp64_oracle():
     """Rows >= 4096 switch the time-parallel GEMMs to the bf16x6 tensor-core path; same 1e-4 bar, and it must agree with
     the CUDA-core path on the same input."""
-    from roomslam_b200 import lstm_model
+    from roomslam_b200 import functional as Fn
     d_model, Q, B, N = 128, 30, 40, 200
     ref64 = TraceToColliderLSTMRef(d_model, Q).eval().double()
     ref64.load_state_dict({k: v.double() for k, v in seeded_state(TraceToColliderLSTMRef(d_model, Q), 5).items()})
@@ -116,11 +116,11 @@ def test_tensor_core_gemm_path_matches_fp64_oracle():
     db, dc, _, dg = run(ref64, traces.double(), mask, wb.double(), wc.double())
     results = {}
     for flag in (True, False):
-        lstm_model.TC_ENABLED = flag
+        Fn.TC_ENABLED = flag
         try:
             results[flag] = run(model, traces.cuda(), mask.cuda(), wb.cuda(), wc.cuda())
         finally:
-            lstm_model.TC_ENABLED = True
+            Fn.TC_ENABLED = True
     for flag, (gb, gc, _, gg) in results.items():
         assert rel_err(gb.cpu(), db) < TOL and rel_err(gc.cpu(), dc) < TOL, flag
         worst = max((rel_err(gg[k].cpu(), dg[k]), k) for k in dg)
