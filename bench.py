@@ -527,6 +527,11 @@ def run_next_rows(args):
 
 
 
+# DRAM bytes per launch of the training step's kernels at the benchmark shape (8192 traces x 500 steps per GPU, bf16), from
+# `ncu --set full` captures of tools/step_once.py 8192 (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_step_kernels_ncu.md)
+NCU_TRAFFIC_B8192 = {"rec_bwd_bf16_kernel": 20.947e9}
+
+
 def train_roofline(kernel_ms, B, pk, precision):
     """Roofline object for the kernel with the largest share of the training step."""
     if not kernel_ms:
@@ -535,12 +540,20 @@ def train_roofline(kernel_ms, B, pk, precision):
     if flops <= 0 or ms <= 0:
         return None
     ach = flops / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": ach / pk["tflops_sustained"], "traffic": None, "kernel": name, "kernel_ms": ms, "launches": calls,
-            "algorithmic_flops": flops,
-            "note": "dominant kernel of the training step by CUDA-event time; in practice it is bound by the HBM traffic of "
-                    "saved activations (DESIGN.md 4.2), the tensor figure is the algorithmic-FLOP view SURVEY.md 8(d) asks for",
-            "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)"}
+    out = {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+           "frac": ach / pk["tflops_sustained"], "traffic": None, "kernel": name, "kernel_ms": ms, "launches": calls,
+           "algorithmic_flops": flops,
+           "note": "dominant kernel of the training step by CUDA-event time; the tensor figure is the algorithmic-FLOP view "
+                   "SURVEY.md 8(d) asks for. In practice the kernel is bound by the HBM traffic of saved activations "
+                   "(DESIGN.md 4.2): see hbm_view",
+           "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)"}
+    if precision == "bf16" and B == TRAIN_BATCH and name in NCU_TRAFFIC_B8192:
+        per_launch = NCU_TRAFFIC_B8192[name]
+        gbs = per_launch / (ms / calls / 1e3) / 1e9
+        out["traffic"] = per_launch
+        out["hbm_view"] = {"bytes_per_launch": per_launch, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": gbs / pk["hbm_gbs"], "source": "ncu --set full, one capture per launch (profiles/r1_step_kernels_ncu.md)"}
+    return out
 
 
 def main():
