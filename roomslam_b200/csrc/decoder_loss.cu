@@ -179,8 +179,8 @@ extern "C" int rs_heads_split_f32(const float* raw, int B, int N, int C, float* 
                                   float* orient, float* valid, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(raw && cls && pos && size && orient && valid, "rs_heads_split_f32: null pointer");
-    if (B == 0) return 0;
     heads_split_kernel<<<blocks_for((long long)B * N * (C + 6)), 256, 0, stream>>>(raw, B, N, C, cls, pos, size, orient, valid);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
@@ -192,8 +192,8 @@ extern "C" int rs_heads_merge_bwd_f32(const float* raw, int B, int N, int C, con
                                       void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(raw && d_raw, "rs_heads_merge_bwd_f32: null pointer");
-    if (B == 0) return 0;
     heads_merge_kernel<<<blocks_for((long long)B * N * (C + 6)), 256, 0, stream>>>(raw, B, N, C, d_cls, d_pos, d_size,
                                                                                   d_orient, d_valid, d_raw);
                                                                                   rs::count_launch();
@@ -204,8 +204,8 @@ extern "C" int rs_heads_merge_bwd_f32(const float* raw, int B, int N, int C, con
 extern "C" int rs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (n == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(dy && y && dx, "rs_relu_bwd_f32: null pointer");
-    if (n == 0) return 0;
     relu_bwd_kernel<<<blocks_for(n), 256, 0, stream>>>(dy, y, dx, n);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
@@ -215,8 +215,8 @@ extern "C" int rs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64
 extern "C" int rs_relu_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (n == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(dy && y && dx, "rs_relu_bwd_bf16: null pointer");
-    if (n == 0) return 0;
     relu_bwd_bf16_kernel<<<blocks_for(n), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
                                                             static_cast<__nv_bfloat16*>(dx), n);
     rs::count_launch();

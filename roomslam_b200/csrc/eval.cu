@@ -254,9 +254,9 @@ extern "C" int rs_eval_pairs(const float* pred_boxes, const float* pred_logits, 
                              const int* n_match, float iou_thresh, double* workspace, double* counts, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(pred_boxes && pred_logits && gt_boxes && gt_labels && gt_valid && match_pred && match_slot && n_match && workspace &&
                    counts, "rs_eval_pairs: null pointer");
-    if (B == 0) return 0;
     eval_pairs_kernel<<<B, 32, 0, stream>>>(pred_boxes, pred_logits, gt_boxes, reinterpret_cast<const long long*>(gt_labels), gt_valid,
                                             Q, M, Q < M ? Q : M, match_pred, match_slot, n_match, iou_thresh, workspace);
     rs::count_launch();
@@ -270,9 +270,9 @@ extern "C" int rs_nms_3d(const float* pred_boxes, const float* pred_logits, int 
                          int* keep_idx, int* n_keep, float* conf, int* label, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(pred_boxes && pred_logits && keep_idx && n_keep && conf && label, "rs_nms_3d: null pointer");
     RS_REQUIRE(Q >= 1 && Q <= MAXQ, "rs_nms_3d: need 1 <= Q <= %d", MAXQ);
-    if (B == 0) return 0;
     nms_kernel<<<B, 32, 0, stream>>>(pred_boxes, pred_logits, Q, conf_thr, nms_thr, keep_idx, n_keep, conf, label);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
@@ -284,9 +284,9 @@ extern "C" int rs_ap_flags(const float* pred_boxes, const float* pred_logits, co
                            int* n_gt, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(pred_boxes && pred_logits && gt_boxes && gt_labels && gt_valid && flags && conf && label && n_gt, "rs_ap_flags: null pointer");
     RS_REQUIRE(Q >= 1 && Q <= MAXQ && M >= 1 && M <= MAXM, "rs_ap_flags: need Q <= %d and M <= %d", MAXQ, MAXM);
-    if (B == 0) return 0;
     ap_flags_kernel<<<B, 32, 0, stream>>>(pred_boxes, pred_logits, gt_boxes, reinterpret_cast<const long long*>(gt_labels), gt_valid, Q,
                                           M, iou_thr, flags, conf, label, n_gt);
     rs::count_launch();
@@ -300,10 +300,10 @@ extern "C" int rs_slot_eval(const float* class_logits, const float* positions, c
                             double* workspace, double* counts, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (n_slots == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(class_logits && positions && sizes && validity_logits && t_classes && t_positions && t_sizes && t_valid && conf &&
                    label && flag && n_gt && workspace && counts, "rs_slot_eval: null pointer");
     RS_REQUIRE(C >= 1 && C <= 64 && n_slots >= 0, "rs_slot_eval: bad sizes");
-    if (n_slots == 0) return 0;
     long long blocks = (n_slots + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     slot_eval_kernel<<<(int)blocks, 256, 0, stream>>>(class_logits, positions, sizes, validity_logits,

@@ -578,10 +578,10 @@ extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk
                               void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (n_blocks == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(A && W && C && a_kchunk, "rs_blk_gemm_nt: null pointer");
     RS_REQUIRE(k_blocks >= 1 && k_blocks <= NT_MAX_KB && n_tiles >= 1, "rs_blk_gemm_nt: 1 <= k_blocks <= %d", NT_MAX_KB);
     RS_REQUIRE(a_cols % 8 == 0 && c_cols % 8 == 0 && n_blocks < (1ll << 31), "rs_blk_gemm_nt: bad shape");
-    if (n_blocks == 0) return 0;
     NtParams p = {};
     p.A = static_cast<const uint8_t*>(A); p.a_block_bytes = a_cols * 256;
     for (int i = 0; i < k_blocks; ++i) {

@@ -270,12 +270,12 @@ extern "C" int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_
                                const float* bias, int64_t M, int N, int K, int flags, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (M == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0, "rs_gemm_bf16_nt: bad arguments");
     RS_REQUIRE(K % BK == 0 && N % BN == 0, "rs_gemm_bf16_nt: need K %% 64 == 0 and N %% 128 == 0 (got N=%d K=%d)", N, K);
     RS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "rs_gemm_bf16_nt: leading dimensions must be multiples of 8");
     const bool out_f32 = flags & RS_GEMM_OUT_F32;
     RS_REQUIRE(M < (1ll << 31), "rs_gemm_bf16_nt: M too large");
-    if (M == 0) return 0;
     CUtensorMap ta, tb, tc;
     if (rs::make_tmap_2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, M, lda * 2, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (rs::make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb * 2, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
@@ -304,11 +304,11 @@ extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, i
                                    int64_t ldc, int M, int N, int64_t rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (rows == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(A && B && C && M > 0 && N > 0 && rows >= 0, "rs_gemm_bf16_tn_acc: bad arguments");
     RS_REQUIRE(M % BM == 0 && N % BN == 0, "rs_gemm_bf16_tn_acc: need M %% 128 == 0 and N %% 128 == 0 (got %d x %d)", M, N);
     RS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "rs_gemm_bf16_tn_acc: leading dimensions must be multiples of 8");
     RS_REQUIRE(rows < (1ll << 31) && a_rows < (1ll << 31) && b_rows < (1ll << 31), "rs_gemm_bf16_tn_acc: too many rows");
-    if (rows == 0) return 0;
     CUtensorMap ta, tb;
     // clamp the visible rows so that nothing past the last valid pair is read (TMA returns zero out of bounds)
     const int64_t a_vis = (rows + a_row_shift < a_rows) ? rows + a_row_shift : a_rows;

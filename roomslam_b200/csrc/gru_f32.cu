@@ -237,10 +237,10 @@ extern "C" int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int6
                               int64_t o_row0, float* h_n, float* gates, int B, int T, int H, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(H >= 32 && H % 32 == 0 && H <= 512, "rs_gru_fwd_f32: hidden size %d must be a multiple of 32 in [32,512]", H);
     RS_REQUIRE(P || (x && I >= 1 && I <= 4 && w_ih), "rs_gru_fwd_f32: layers with input size > 4 need the projection P");
     RS_REQUIRE(w_hh_t && b_hh && b_ih && out && h_n && B >= 0 && T >= 0, "rs_gru_fwd_f32: bad arguments");
-    if (B == 0) return 0;
     if (T == 0) {
         RS_CUDA_OK(cudaMemsetAsync(h_n, 0, sizeof(float) * 2 * (size_t)B * H, stream));
         return 0;
@@ -279,9 +279,9 @@ extern "C" int rs_gru_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows
                               int B, int T, int H, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(H >= 32 && H % 32 == 0 && H <= 512, "rs_gru_bwd_f32: hidden size %d must be a multiple of 32 in [32,512]", H);
     RS_REQUIRE(gates && out && w_hh && dGx && dGh && B >= 0 && T >= 0, "rs_gru_bwd_f32: bad arguments");
-    if (B == 0 || T == 0) return 0;
     const bool wsmem = (size_t)H * 3 * H * 4 <= 200 * 1024;
     const int S = (H <= 128) ? 2 : 1024 / H >= 2 ? 2 : 1;
     const bool big = B > 148;

@@ -435,9 +435,9 @@ extern "C" int rs_lstm_fwd_f32(const float* P, int64_t p_ld, int64_t p_rows, int
                                void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(H >= 32 && H % 32 == 0 && H <= 256, "rs_lstm_fwd_f32: hidden size %d must be a multiple of 32 in [32,256]", H);
     RS_REQUIRE(P && w_hh && w_hh_t && out && B >= 0 && T >= 0, "rs_lstm_fwd_f32: bad arguments");
-    if (B == 0 || T == 0) return 0;
     if (H == 32 || H == 64) {                               // weights in registers
         SeqF rp = mkf(P, p_ld, p_rows, p_row0), ro = mkf(out, o_ld, o_rows, o_row0);
         if (H == 64) launch_reg_fwd<64>(rp, w_hh, ro, saved, B, T, stream);
@@ -469,9 +469,9 @@ extern "C" int rs_lstm_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_row
                                int H, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(H >= 32 && H % 32 == 0 && H <= 256, "rs_lstm_bwd_f32: hidden size %d must be a multiple of 32 in [32,256]", H);
     RS_REQUIRE(d_out && saved && w_hh && dG && B >= 0 && T >= 0, "rs_lstm_bwd_f32: bad arguments");
-    if (B == 0 || T == 0) return 0;
     if (H == 32 || H == 64) {
         SeqF rdo = mkf(d_out, do_ld, do_rows, do_row0), rg = mkf(dG, g_ld, g_rows, g_row0);
         if (H == 64) launch_reg_bwd<64>(rdo, saved, w_hh, rg, B, T, stream);

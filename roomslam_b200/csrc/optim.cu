@@ -52,8 +52,8 @@ extern "C" int rs_adamw_step_f32(float* p, const float* g, float* m, float* v, i
                                  double* sumsq_scratch, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (n == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(p && g && m && v && sumsq_scratch && n >= 0 && step >= 1, "rs_adamw_step_f32: bad arguments");
-    if (n == 0) return 0;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (max_norm > 0.0f) {

@@ -103,6 +103,10 @@ extern "C" int rs_trace_features(const float* pts, const int64_t* offsets, int B
                                  unsigned char* mask, int64_t* lengths, int* unsorted_flag, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) {                                            // empty batch: empty tensors carry null pointers
+        if (unsorted_flag) RS_CUDA_OK(cudaMemsetAsync(unsorted_flag, 0, sizeof(int), stream));
+        return 0;
+    }
     RS_REQUIRE(offsets && feats && mask && lengths && unsorted_flag, "rs_trace_features: null pointer");
     RS_REQUIRE(B >= 0 && max_len >= 2 && out_len >= 1, "rs_trace_features: need max_len >= 2 and out_len >= 1");
     RS_REQUIRE((reinterpret_cast<uintptr_t>(pts) & 15) == 0, "rs_trace_features: points must be 16-byte aligned (x, y, z, t rows)");

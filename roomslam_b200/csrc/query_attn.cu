@@ -401,8 +401,8 @@ extern "C" int rs_trace_stats_f32(const float* traces, int F, const unsigned cha
                                   float* count, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(traces && mean && rms && count && F >= 3 && B >= 0 && N >= 1, "rs_trace_stats_f32: bad arguments");
-    if (B == 0) return 0;
     trace_stats_kernel<<<B, 256, 0, stream>>>(traces, F, mask, N, mean, rms, count);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
@@ -419,11 +419,11 @@ extern "C" int rs_query_attn_fwd_f32(const float* memory, int64_t m_ld, int64_t 
                                      float* anchor, float* summary, float* stats, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(memory && traces && mean && rms && qk && qb && workspace && ctx && anchor && summary && stats,
                "rs_query_attn_fwd_f32: null pointer");
     RS_REQUIRE(D >= 32 && D % 32 == 0 && D <= 256, "rs_query_attn_fwd_f32: d_model %d must be a multiple of 32 in [32,256]", D);
     RS_REQUIRE(Q >= 1 && N >= 1 && splits >= 1 && F >= 3 && m_ld % 4 == 0, "rs_query_attn_fwd_f32: bad sizes");
-    if (B == 0) return 0;
     const int chunks = (N + TC - 1) / TC;
     const int tps = ((chunks + splits - 1) / splits) * TC;
     const int qtiles = (Q + QT - 1) / QT;
@@ -446,11 +446,11 @@ extern "C" int rs_query_attn_bwd_f32(const float* memory, int64_t m_ld, int64_t 
                                      int64_t dm_row0, float* dq_part, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(memory && traces && mean && rms && count && qk && qb && ctx && anchor && stats && d_ctx && d_anchor && d_memory &&
                    dq_part, "rs_query_attn_bwd_f32: null pointer");
     RS_REQUIRE(D >= 32 && D % 32 == 0 && D <= 256, "rs_query_attn_bwd_f32: d_model %d must be a multiple of 32 in [32,256]", D);
     RS_REQUIRE(Q >= 1 && N >= 1 && splits >= 1 && F >= 3 && m_ld % 4 == 0, "rs_query_attn_bwd_f32: bad sizes");
-    if (B == 0) return 0;
     const int chunks = (N + TC - 1) / TC;
     const int tps = ((chunks + splits - 1) / splits) * TC;
     const int qtiles = (Q + QT - 1) / QT;

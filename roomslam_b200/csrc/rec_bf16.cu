@@ -529,11 +529,11 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
                                const float* b_hn, void* out, void* gates, float* h_n, int B, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE((x != nullptr) != (P != nullptr), "rs_rec_fwd_bf16: exactly one of x (layer 0) and P (deeper layers) must be given");
     RS_REQUIRE(!x || (I >= 1 && I <= 2), "rs_rec_fwd_bf16: the MMA-fused input projection takes 1 or 2 input columns");
     RS_REQUIRE(!P || p_cols == 6 * H, "rs_rec_fwd_bf16: P must have 6H = %d columns", 6 * H);
     RS_REQUIRE(Whh && b_hn && out && h_n && B >= 0 && T >= 0, "rs_rec_fwd_bf16: bad arguments");
-    if (B == 0) return 0;
     if (T == 0) {
         RS_CUDA_OK(cudaMemsetAsync(h_n, 0, sizeof(float) * 2 * (size_t)B * H, stream));
         return 0;
@@ -557,8 +557,8 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
                                void* dG, int B, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(gates && out && WhhT && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
-    if (B == 0 || T == 0) return 0;
     BwdParams p = {};
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);

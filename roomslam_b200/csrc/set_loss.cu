@@ -269,10 +269,10 @@ extern "C" int rs_hungarian_match(const float* pred_boxes, const float* pred_log
                                   float w_box, int* match_pred, int* match_slot, int* match_rank, int* n_match, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(pred_boxes && pred_logits && gt_boxes && gt_labels && gt_valid && match_pred && match_slot && match_rank && n_match,
                "rs_hungarian_match: null pointer");
     RS_REQUIRE(Q >= 1 && Q <= MAXQ && M >= 1 && M <= MAXM, "rs_hungarian_match: need 1 <= Q <= %d queries and 1 <= M <= %d slots", MAXQ, MAXM);
-    if (B == 0) return 0;
     const size_t smem = (size_t)Q * M * sizeof(float);
     RS_CUDA_OK(cudaFuncSetAttribute(hungarian_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hungarian_match_kernel<<<B, 32, smem, stream>>>(pred_boxes, pred_logits, gt_boxes, reinterpret_cast<const long long*>(gt_labels),
@@ -289,6 +289,11 @@ extern "C" int rs_set_loss_f32(const float* pred_boxes, const float* pred_logits
                                float* g_l1, float* g_giou, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (B == 0) {                                            // empty batch: all losses are zero (train.py:146-147,165-166)
+        RS_REQUIRE(losses, "rs_set_loss_f32: null pointer");
+        RS_CUDA_OK(cudaMemsetAsync(losses, 0, 4 * sizeof(float), stream));
+        return 0;
+    }
     RS_REQUIRE(pred_boxes && pred_logits && gt_boxes && gt_labels && match_pred && match_slot && n_match && workspace && losses &&
                    g_logits && g_l1 && g_giou, "rs_set_loss_f32: null pointer");
     RS_REQUIRE(Q >= 1 && M >= 1 && B >= 0, "rs_set_loss_f32: bad sizes");

@@ -105,8 +105,8 @@ extern "C" int rs_sgemm(const float* A, int64_t a_sm, int64_t a_sk, const float*
                         int64_t ldc, const float* bias, int M, int N, int K, int flags, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (M == 0 || N == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0, "rs_sgemm: bad arguments");
-    if (M == 0 || N == 0) return 0;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
     int k_per_split = K;
     const bool relu = flags & RS_GEMM_RELU;
@@ -135,9 +135,9 @@ extern "C" int rs_sgemm(const float* A, int64_t a_sm, int64_t a_sk, const float*
 extern "C" int rs_colsum_f32(const float* A, int64_t lda, int M, int N, float* out, int accumulate, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
-    RS_REQUIRE(A && out && M >= 0 && N > 0, "rs_colsum_f32: bad arguments");
+    RS_REQUIRE((A || M == 0) && out && M >= 0 && N > 0, "rs_colsum_f32: bad arguments");
     if (!accumulate) RS_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
-    if (M == 0) return 0;
+    if (M == 0) return 0;        // the column sums of an empty matrix are zero
     int slabs = (M + 2047) / 2048;
     if (slabs > 128) slabs = 128;
     const int rows_per_block = (M + slabs - 1) / slabs;

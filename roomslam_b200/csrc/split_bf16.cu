@@ -72,11 +72,11 @@ extern "C" int rs_split_bf16x6(const float* x, int64_t ld, int64_t rows, int col
                                void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
+    if (rows == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(x && out && rows >= 0 && cols >= 1, "rs_split_bf16x6: bad arguments");
     RS_REQUIRE(kpad % 8 == 0 && kpad >= cols && ld_out >= 6 * (int64_t)kpad && ld_out % 8 == 0,
                "rs_split_bf16x6: kpad must be a multiple of 8 >= cols and ld_out >= 6 * kpad (multiple of 8)");
     RS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "rs_split_bf16x6: output must be 16-byte aligned");
-    if (rows == 0) return 0;
     const long long total = rows * (kpad / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;

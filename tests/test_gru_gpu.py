@@ -153,7 +153,7 @@ def test_fp32_mode_tensor_core_gemms_keep_parity():
             loss["total"].backward()
         finally:
             Fn.TC_ENABLED = True
-        assert abs(float(loss["total"]) - float(lr["total"])) < 1e-4 * abs(float(lr["total"]))
+        assert abs(float(loss["total"].detach()) - float(lr["total"].detach())) < 1e-4 * abs(float(lr["total"].detach()))
         for k, p in model.named_parameters():
             err = float((p.grad.double().cpu() - want[k]).abs().max() / max(1.0, float(want[k].abs().max())))
             assert err < 1e-4, (flag, k, err)
