@@ -58,3 +58,34 @@ def load_dir(data_dir: str, seq_len: int = 500, max_objects: int = 10) -> Tuple[
                 tgt["orientations"][i, k] = float(o.get("orientation", 0.0))
                 tgt["valid"][i, k] = 1.0
     return x, tgt
+
+
+# ---- the shipped benchmark's file formats (src/benchmark/dataloader.py): host-side plumbing for the BiLSTM pipeline ----
+COLLIDER_LABELS = {"BLOCK": 0, "LOW": 1, "MID": 2, "HIGH": 3}            # dataloader.py:67-72
+
+
+def load_trace_points(path: str) -> torch.Tensor:
+    """``*_data_*.json``: list of {timestamp, x, y, z} -> (N, 4) fp32 rows (x, y, z, timestamp), the input of
+    ``preprocess.trace_features`` (what dataloader.py:420 builds before the kinematic features)."""
+    pts = json.load(open(path))
+    return torch.tensor([[p["x"], p["y"], p["z"], p["timestamp"]] for p in pts], dtype=torch.float32).reshape(-1, 4)
+
+
+def colliders_to_targets(colliders, max_colliders: int = 50) -> Dict[str, torch.Tensor]:
+    """List of collider dicts ({label, center{x,y,z}, size{x,y,z}}) -> {"boxes" (M, 6), "labels" (M,) int64 (-1 padded),
+    "valid_mask" (M,) bool}: the target format of dataloader.py:459-507 (unknown labels map to 0, missing fields to 0.0,
+    colliders beyond max_colliders are dropped)."""
+    boxes = torch.zeros(max_colliders, 6)
+    labels = torch.full((max_colliders,), -1, dtype=torch.long)
+    valid = torch.zeros(max_colliders, dtype=torch.bool)
+    for i, col in enumerate(colliders[:max_colliders]):
+        c, s = col.get("center", {}), col.get("size", {})
+        boxes[i] = torch.tensor([c.get("x", 0.0), c.get("y", 0.0), c.get("z", 0.0), s.get("x", 0.0), s.get("y", 0.0), s.get("z", 0.0)])
+        labels[i] = COLLIDER_LABELS.get(col.get("label", "BLOCK"), 0)
+        valid[i] = True
+    return {"boxes": boxes, "labels": labels, "valid_mask": valid}
+
+
+def load_colliders(path: str, max_colliders: int = 50) -> Dict[str, torch.Tensor]:
+    """``colliders.json`` ({"colliders": [...]}, dataset/train/colliders.json:1-19) -> targets of one scene."""
+    return colliders_to_targets(json.load(open(path))["colliders"], max_colliders)

@@ -79,3 +79,17 @@ def test_grad_reducer_two_ranks_gloo(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_collider_targets_match_the_reference_loader():
+    """roomslam_b200.data.colliders_to_targets against the reference's own _process_colliders on the real collider file
+    and on edge cases (tests/golden/colliders.npz, oracle/make_golden_colliders.py)."""
+    import json
+    import os
+    import numpy as np
+    from roomslam_b200 import data
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "colliders.npz"))
+    for name in ("train", "edge", "overflow", "none"):
+        t = data.colliders_to_targets(json.loads(str(g[f"{name}_json"])))
+        assert np.array_equal(t["boxes"].numpy(), g[f"{name}_boxes"]), name
+        assert np.array_equal(t["labels"].numpy(), g[f"{name}_labels"]) and np.array_equal(t["valid_mask"].numpy(), g[f"{name}_valid"])

@@ -50,3 +50,38 @@ def test_training_loop_reduces_the_set_loss_and_evaluates():
     assert keep.shape == (4, 30) and int(n.max()) <= 30
     mAP, aps = mean_average_precision(out["pred_boxes"], out["pred_classes"], targets["boxes"], targets["labels"], targets["valid_mask"])
     assert 0.0 <= mAP <= 1.0
+
+
+def test_real_traces_and_real_colliders_overfit():
+    """The upstream data end to end: three recorded traces (tests/golden/features.npz) and the recorded collider set
+    (tests/golden/colliders.npz) -> features -> BiLSTM -> Hungarian set loss; 60 AdamW steps must fit the scene."""
+    import json
+    import os
+    from roomslam_b200 import data, preprocess
+    from roomslam_b200.evaluation import evaluate_metrics
+    from roomslam_b200.lstm_model import build_model
+    from roomslam_b200.set_loss import SetCriterion
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    f = np.load(os.path.join(gdir, "features.npz"))
+    c = np.load(os.path.join(gdir, "colliders.npz"))
+    batch = preprocess.trace_features([f[f"real{k}_points"] for k in range(3)], max_len=800)
+    x, mask = batch["traces"], batch["trace_mask"]
+    assert x.shape == (3, 800, 11) and bool(mask.all())
+    tgt = data.colliders_to_targets(json.loads(str(c["train_json"])))
+    targets = {k: v.unsqueeze(0).expand(3, *v.shape).contiguous().cuda() for k, v in tgt.items()}
+    torch.manual_seed(1)
+    model = build_model(num_queries=30, d_model=128, model_type="lstm", dropout=0.0).cuda().train()
+    crit = SetCriterion({"class_loss": 2.0, "l1_loss": 5.0, "giou_loss": 2.0})
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-3, weight_decay=1e-4)
+    hist = []
+    for it in range(60):
+        opt.zero_grad()
+        losses = crit(model(x, mask), targets)
+        losses["total_loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        hist.append(float(losses["total_loss"].detach()))
+    assert np.isfinite(hist[-1]) and hist[-1] < 0.6 * hist[0], (hist[0], hist[-1])
+    loader = [{"traces": x.cpu(), "trace_mask": mask.cpu(), **{k: v.cpu() for k, v in targets.items()}}]
+    m = evaluate_metrics(model, loader, "cuda")
+    assert m["tp"] + m["fp"] == 33 and m["fn"] == 0 and m["cls_acc"] > 0.5
