@@ -168,6 +168,13 @@ int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, co
 int rs_trace_features(const float* pts, const int64_t* offsets, int B, int max_len, int out_len, float* feats,
                       unsigned char* mask, int64_t* lengths, int* unsorted_flag, void* stream);
 
+/* Uniform-rate resampling + windowing of recorded traces into the GRU's (W, seq_len, 2) input (floor plane x, z).
+ * pts: [total, 4] fp64 rows (x, y, z, timestamp), time-sorted per trace; offsets [B+1]; window w covers samples
+ * win_start[w] .. win_start[w]+seq_len-1 of trace win_trace[w] on the grid numpy.arange(t_first, t_last, step);
+ * values = numpy.interp in fp64, rounded to fp32: bit-identical to the numpy procedure (oracle/resample_ref.py). */
+int rs_resample_windows_f64(const double* pts, const int64_t* offsets, const int64_t* win_trace, const int64_t* win_start,
+                            int64_t n_windows, int seq_len, double step, float* out, void* stream);
+
 /* ---- the shipped BiLSTM + query-decoder model (src/benchmark/model.py:6-153), fp32 ------------ */
 /* One bidirectional LSTM layer (replaces torch.nn.LSTM, model.py:16-23,49).  P: [.., 2*4H] = W_ih x + b_ih + b_hh for both
  * directions (gate rows i|f|g|o); w_hh: [2][4H][H] and its transpose w_hh_t: [2][H][4H]; out: [.., 2H]; saved: [2][B][T][5][H] (i, f, g, o, c) or NULL. */

@@ -97,6 +97,48 @@ trace_features_kernel(const float4* __restrict__ pts, const long long* __restric
     }
 }
 
+
+// ---- uniform-rate resampling + windowing for the GRU input (decision D14: README.md:145 "10 Hz", windows of seq_len) ----
+// One thread per output sample: t_i of numpy's arange(t_first, t_last, 1/hz) (element 0 = start, 1 = start + step,
+// i >= 2: start + i * ((start + step) - start), as numpy fills it), binary search of the bracketing source points, and
+// np.interp's  slope * (t - t_j) + f_j  in fp64 without FMA contraction, for the floor-plane coordinates (x, z).
+__global__ void __launch_bounds__(256)
+resample_windows_kernel(const double* __restrict__ pts, const long long* __restrict__ offsets, const long long* __restrict__ win_trace,
+                        const long long* __restrict__ win_start, long long total, int seq_len, double step,
+                        float* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long w = e / seq_len;
+        const long long i = win_start[w] + e % seq_len;
+        const long long b = win_trace[w];
+        const double* tr = pts + offsets[b] * 4;
+        const long long n = offsets[b + 1] - offsets[b];
+        const double start = tr[3];
+        const double next = __dadd_rn(start, step);
+        const double delta = __dsub_rn(next, start);
+        const double t = i == 0 ? start : (i == 1 ? next : __dadd_rn(start, __dmul_rn((double)i, delta)));
+        // largest j with t_j <= t (t lies inside [t_0, t_{n-1}) by construction)
+        long long lo = 0, hi = n - 1;
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (tr[mid * 4 + 3] <= t) lo = mid; else hi = mid;
+        }
+        float v[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int col = c == 0 ? 0 : 2;                        // x and z: the floor plane (y is height)
+            const double f0 = tr[lo * 4 + col], x0 = tr[lo * 4 + 3];
+            double r = f0;
+            if (t != x0 && lo + 1 < n) {
+                const double slope = __ddiv_rn(__dsub_rn(tr[(lo + 1) * 4 + col], f0), __dsub_rn(tr[(lo + 1) * 4 + 3], x0));
+                r = __dadd_rn(__dmul_rn(slope, __dsub_rn(t, x0)), f0);
+            }
+            v[c] = (float)r;
+        }
+        out[e * 2] = v[0];
+        out[e * 2 + 1] = v[1];
+    }
+}
+
 }  // namespace
 
 extern "C" int rs_trace_features(const float* pts, const int64_t* offsets, int B, int max_len, int out_len, float* feats,
@@ -119,6 +161,23 @@ extern "C" int rs_trace_features(const float* pts, const int64_t* offsets, int B
     trace_features_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(pts),
                                                            reinterpret_cast<const long long*>(offsets), B, max_len, out_len, feats,
                                                            mask, reinterpret_cast<long long*>(lengths), unsorted_flag, vec_ok);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_resample_windows_f64(const double* pts, const int64_t* offsets, const int64_t* win_trace, const int64_t* win_start,
+                                       int64_t n_windows, int seq_len, double step, float* out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    if (n_windows == 0) return 0;        // nothing to do: empty tensors carry null pointers
+    RS_REQUIRE(pts && offsets && win_trace && win_start && out && seq_len >= 1 && step > 0.0, "rs_resample_windows_f64: bad arguments");
+    const long long total = (long long)n_windows * seq_len;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    resample_windows_kernel<<<(int)blocks, 256, 0, stream>>>(pts, reinterpret_cast<const long long*>(offsets),
+                                                             reinterpret_cast<const long long*>(win_trace),
+                                                             reinterpret_cast<const long long*>(win_start), total, seq_len, step, out);
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -80,3 +80,31 @@ def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3
     if check_sorted and int(flag.item()):
         raise ValueError("trace_features: a trace is not sorted by timestamp (pass sort=True)")
     return {"traces": feats, "trace_mask": mask.bool(), "lengths": lengths}
+
+
+def resample_windows(traces: Sequence, seq_len: int = 500, hz: float = 10.0):
+    """Recorded traces -> the GRU model's input: list of (N_i, 4) arrays with rows (x, y, z, timestamp) (float64 keeps
+    the JSON precision) -> {"windows": (W, seq_len, 2) fp32 on the GPU (floor plane x, z, resampled to `hz` by linear
+    interpolation, cut into non-overlapping windows), "trace": (W,) index of the source trace}.  Bit-identical to
+    numpy.arange + numpy.interp (rs_resample_windows_f64)."""
+    parts, offs, win_trace, win_start = [], [0], [], []
+    step = 1.0 / hz
+    for b, t in enumerate(traces):
+        t = torch.as_tensor(np.asarray(t, dtype=np.float64) if not torch.is_tensor(t) else t, dtype=torch.float64).reshape(-1, 4).cpu()
+        if t.shape[0] >= 2:
+            t = t[torch.sort(t[:, 3], stable=True).indices]
+            n = int(np.ceil((float(t[-1, 3]) - float(t[0, 3])) / step))          # len(numpy.arange(t0, t_last, step))
+            for s in range(0, n - seq_len + 1, seq_len):
+                win_trace.append(b)
+                win_start.append(s)
+        parts.append(t)
+        offs.append(offs[-1] + t.shape[0])
+    W = len(win_trace)
+    out = torch.empty(W, seq_len, 2, dtype=torch.float32, device="cuda")
+    if W:
+        packed = torch.cat(parts).cuda().contiguous()
+        dev = lambda v: torch.tensor(v, dtype=torch.int64, device="cuda")      # noqa: E731
+        o, wt, ws = dev(offs), dev(win_trace), dev(win_start)
+        _lib.call("rs_resample_windows_f64", packed.data_ptr(), o.data_ptr(), wt.data_ptr(), ws.data_ptr(), W, seq_len, step,
+                  out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return {"windows": out, "trace": torch.tensor(win_trace, dtype=torch.int64)}

@@ -101,3 +101,22 @@ def test_auto_sort_only_when_needed(golden):
     want, wmask = features_ref.collate([features_ref.process_points(pts), features_ref.process_points(golden["two_points"])])
     assert np.array_equal(bits(auto["traces"].cpu().numpy()), bits(want))
     assert np.array_equal(auto["trace_mask"].cpu().numpy(), wmask)
+
+
+def test_resample_windows_bit_exact(golden):
+    """Recorded traces -> 10 Hz, T = 500 floor-plane windows for the GRU: GPU kernel against numpy.arange + numpy.interp."""
+    from oracle import resample_ref
+    from roomslam_b200 import preprocess
+    rng = np.random.default_rng(2)
+    traces = [golden[f"real{k}_points"].astype(np.float64) for k in range(3)]
+    t = np.cumsum(rng.uniform(0.001, 0.3, 4000)) + 1234.5678
+    traces.append(np.stack([rng.normal(0, 3, 4000), rng.normal(1.6, .1, 4000), rng.normal(0, 3, 4000), t], 1)[rng.permutation(4000)])
+    traces.append(np.zeros((1, 4)))                                        # too short: no windows
+    for seq_len, hz in ((500, 10.0), (64, 7.3), (50, 30.0)):
+        out = preprocess.resample_windows(traces, seq_len=seq_len, hz=hz)
+        want = [resample_ref.resample_windows(tr, seq_len, hz) for tr in traces]
+        idx = np.concatenate([np.full(len(w), b) for b, w in enumerate(want)])
+        want = np.concatenate(want)
+        assert want.shape[0] > 0 and tuple(out["windows"].shape) == want.shape
+        assert np.array_equal(out["trace"].numpy(), idx)
+        assert np.array_equal(bits(out["windows"].cpu().numpy()), bits(want))
