@@ -204,7 +204,7 @@ def run_ours(args):
     import torch.distributed as dist
     from roomslam_b200 import RoomSLAM, OccupancyHeatmapBaseline, synth, _lib
     from roomslam_b200 import functional as F_
-    from roomslam_b200.train_utils import FlatParams, GradReducer, FusedAdamW
+    from roomslam_b200.train_utils import FlatParams, GradReducer, FusedAdamW, HostBatchPrefetcher
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,11 +255,17 @@ def run_ours(args):
     def step_resident():
         step(x_dev, tgt_dev)
 
+    prefetch = HostBatchPrefetcher("cuda")
+
     def step_e2e():
-        x = x_host.to("cuda", non_blocking=True)
-        tgt = {k: v.to("cuda", non_blocking=True) for k, v in tgt_host.items()}
+        # public-API training loop: every step copies ITS batch from pinned host memory (one copy per step, started while
+        # the previous step computes) and reads its loss back to the host
+        if not prefetch.has_pending:
+            prefetch.submit(x_host, tgt_host)
+        x, tgt = prefetch.get()
+        prefetch.submit(x_host, tgt_host)                                      # next step's batch: overlaps this step
         loss = step(x, tgt)
-        loss_host[0:1].copy_(loss.detach().reshape(1), non_blocking=False)     # device -> host read of the loss
+        loss_host[0:1].copy_(loss.detach().reshape(1), non_blocking=True)      # device -> host read of the loss (pinned)
 
     sampler = ClockSampler(local)
     if rank == 0:

@@ -148,3 +148,42 @@ class FusedAdamW:
         _lib.call("rs_adamw_step_f32", f.flat.data_ptr(), f.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), f.numel,
                   self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t, grad_scale, self.max_norm or 0.0,
                   self.scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+
+class HostBatchPrefetcher:
+    """Double-buffered host -> device staging: ``submit`` starts the copy of a (pinned) host batch on a side stream,
+    ``get`` hands the device tensors to the current stream once the copy has landed.  Submitting batch k+1 right after
+    getting batch k overlaps its PCIe transfer with step k's kernels (the upstream loop copies synchronously at the top
+    of every iteration, src/benchmark/train.py:199-203)."""
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pending = None
+
+    def submit(self, x_host: torch.Tensor, tgt_host: dict) -> None:
+        if self._pending is not None:
+            raise RuntimeError("HostBatchPrefetcher: get() the previous batch before submitting another one")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))      # buffers freed by the compute stream are reusable
+        with torch.cuda.stream(self.stream):
+            x = x_host.to(self.device, non_blocking=True)
+            tgt = {k: v.to(self.device, non_blocking=True) for k, v in tgt_host.items()}
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._pending = (x, tgt, done)
+
+    def get(self):
+        if self._pending is None:
+            raise RuntimeError("HostBatchPrefetcher: nothing submitted")
+        x, tgt, done = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(done)
+        x.record_stream(cur)
+        for v in tgt.values():
+            v.record_stream(cur)
+        return x, tgt
+
+    @property
+    def has_pending(self) -> bool:
+        return self._pending is not None

@@ -97,3 +97,24 @@ def test_heatmap_shards_sum_to_the_whole():
         o, s, d = b.bin(shard.contiguous())
         acc_o += o; acc_s += s; acc_d += d
     assert torch.equal(acc_o, occ) and torch.equal(acc_s, stat) and acc_d == nd
+
+
+def test_host_batch_prefetcher_round_trip():
+    from roomslam_b200 import synth
+    from roomslam_b200.train_utils import HostBatchPrefetcher
+    pf = HostBatchPrefetcher("cuda")
+    batches = []
+    for seed in range(3):
+        x, tgt = synth.make_sample(64, 500, 10, seed=seed)
+        batches.append((x.pin_memory(), {k: v.pin_memory() for k, v in tgt.items()}))
+    pf.submit(*batches[0])
+    for k in range(3):
+        x, tgt = pf.get()
+        if k + 1 < 3:
+            pf.submit(*batches[k + 1])
+        y = (x * 2).sum()                                   # consumer work on the current stream
+        assert torch.equal(x.cpu(), batches[k][0]) and all(torch.equal(tgt[n].cpu(), batches[k][1][n]) for n in tgt)
+        assert torch.isfinite(y)
+    assert not pf.has_pending
+    with pytest.raises(RuntimeError):
+        pf.get()
