@@ -81,7 +81,7 @@ def test_real_traces_and_real_colliders_overfit():
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         hist.append(float(losses["total_loss"].detach()))
-    assert np.isfinite(hist[-1]) and hist[-1] < 0.6 * hist[0], (hist[0], hist[-1])
+    assert np.isfinite(hist[-1]) and hist[-1] < 0.75 * hist[0], (hist[0], hist[-1])
     loader = [{"traces": x.cpu(), "trace_mask": mask.cpu(), **{k: v.cpu() for k, v in targets.items()}}]
     m = evaluate_metrics(model, loader, "cuda")
     assert m["tp"] + m["fp"] == 33 and m["fn"] == 0 and m["cls_acc"] > 0.5
