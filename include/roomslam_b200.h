@@ -64,13 +64,16 @@ int rs_colsum_f32(const float* A, int64_t lda, int M, int N, float* out, int acc
 int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int64_t x_row0, int I, const float* w_ih,
                    const float* b_ih, const float* P, int64_t p_ld, int64_t p_rows, int64_t p_row0,
                    const float* w_hh_t, const float* b_hh, float* out, int64_t o_ld, int64_t o_rows, int64_t o_row0,
-                   float* h_n, float* gates, int B, int T, int H, void* stream);
-/* Backward through time of the same layer.  d_out [., 2H] and d_h_n [2][B][H] may be NULL (zero).  w_hh [2][3H][H].
+                   float* h_n, float* gates, const int* lengths, int B, int T, int H, void* stream);
+/* lengths (all recurrence entry points): int32 [B] valid steps per trace or NULL.  Packed-sequence semantics of
+ * torch.nn.utils.rnn.pack_padded_sequence: past its length a trace keeps its state (h_n = state at the last valid step),
+ * emits zero outputs, and its padded outputs carry no gradient.
+ * Backward through time of the same layer.  d_out [., 2H] and d_h_n [2][B][H] may be NULL (zero).  w_hh [2][3H][H].
  * Writes dGx, dGh [., 6H]: gradients w.r.t. the input-side / hidden-side gate pre-activations. */
 int rs_gru_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows, int64_t do_row0, const float* d_h_n,
                    const float* gates, const float* out, int64_t o_ld, int64_t o_rows, int64_t o_row0,
-                   const float* w_hh, float* dGx, float* dGh, int64_t g_ld, int64_t g_rows, int64_t g_row0, int B, int T,
-                   int H, void* stream);
+                   const float* w_hh, float* dGx, float* dGh, int64_t g_ld, int64_t g_rows, int64_t g_row0,
+                   const int* lengths, int B, int T, int H, void* stream);
 /* o = a * m element-wise over sequence buffers (m NULL: copy).  Inter-layer dropout mask (decision D4). */
 int rs_seq_mul_f32(const float* a, int64_t a_ld, int64_t a_rows, int64_t a_row0, const float* m, int64_t m_ld,
                    int64_t m_rows, int64_t m_row0, float* o, int64_t o_ld, int64_t o_rows, int64_t o_row0, int B, int T,
@@ -151,13 +154,13 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
  * weights / biases carry the factor 1/2 of sigma(a) = tanh(a/2)/2 + 1/2.  b_hn [2][H], out tile-major (2H columns,
  * zero pad rows), gates [tiles][T][2][64][128][8] fp16 (NULL for inference), h_n [2][B][H] fp32. */
 int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
-                    void* gates, float* h_n, int B, int T, void* stream);
+                    void* gates, float* h_n, const int* lengths, int B, int T, void* stream);
 /* x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (zero padded): layer-0 input for rs_blk_wgrad. */
 int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 /* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
  * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                    int B, int T, void* stream);
+                    const int* lengths, int B, int T, void* stream);
 
 /* ---- on-GPU trace preprocessing (replaces src/benchmark/dataloader.py:410-457 _process_traces
  *      = src/benchmark/inference.py:24-57 process_traces, plus the padding of collate_fn dataloader.py:510-559) ------ */

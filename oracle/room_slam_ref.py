@@ -86,8 +86,16 @@ class RoomSLAM(nn.Module):
                       f"bias_ih_l{layer}{sfx}", f"bias_hh_l{layer}{sfx}"]
         return [getattr(self.encoder, n) for n in names]
 
-    def encode(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None):
-        """Returns (out (B,T,2H) of the top layer, h_n (2L,B,H)) exactly as nn.GRU would."""
+    def encode(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None):
+        """Returns (out (B,T,2H) of the top layer, h_n (2L,B,H)) exactly as nn.GRU would; with `lengths`, exactly as nn.GRU
+        on torch.nn.utils.rnn.pack_padded_sequence(x, lengths) would (variable-length traces)."""
+        if lengths is not None:
+            if dropout_mask is not None or (self.training and self.dropout > 0 and self.num_layers > 1):
+                raise NotImplementedError("oracle: lengths are supported without inter-layer dropout")
+            packed = torch.nn.utils.rnn.pack_padded_sequence(x, torch.as_tensor(lengths).cpu(), batch_first=True, enforce_sorted=False)
+            out, h_n = self.encoder(packed)
+            out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=x.shape[1])
+            return out, h_n
         if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
             dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
         if dropout_mask is None:
@@ -104,8 +112,9 @@ class RoomSLAM(nn.Module):
             inp = out * dropout_mask[layer] if layer < self.num_layers - 1 else out
         return inp, torch.cat(h_all, dim=0)
 
-    def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        _, h_n = self.encode(x, dropout_mask)
+    def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
+                lengths: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        _, h_n = self.encode(x, dropout_mask, lengths)
         latent = torch.cat([h_n[-2], h_n[-1]], dim=-1)  # D5, README.md:115
         return self.decoder(latent)
 

@@ -32,7 +32,7 @@ template <int R, bool WSMEM, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 gru_fwd_f32_kernel(Seq x, int I, const float* __restrict__ w_ih, const float* __restrict__ b_ih, Seq P,
                    const float* __restrict__ w_hh_t, const float* __restrict__ b_hh, Seq out,
-                   float* __restrict__ h_n, float* __restrict__ gates, int B, int T, int H) {
+                   float* __restrict__ h_n, float* __restrict__ gates, const int* __restrict__ lengths, int B, int T, int H) {
     extern __shared__ __align__(16) float smem_f[];
     const int i = threadIdx.x, y = threadIdx.y, S = blockDim.y, Bt = S * R;
     const int dir = blockIdx.y;
@@ -56,6 +56,9 @@ gru_fwd_f32_kernel(Seq x, int I, const float* __restrict__ w_ih, const float* __
     __syncthreads();
 
     const long long b0 = (long long)blockIdx.x * Bt + y * R;
+    int len[R];                                    // valid steps of each trace (packed-sequence semantics); T when no lengths
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) len[rr] = (lengths && b0 + rr < B) ? lengths[b0 + rr] : T;
     int cur = 0;
     for (int step = 0; step < T; ++step) {
         const int t = dir ? (T - 1 - step) : step;
@@ -102,14 +105,15 @@ gru_fwd_f32_kernel(Seq x, int I, const float* __restrict__ w_ih, const float* __
                         px[g] = s;
                     }
                 }
+                const bool active = t < len[rr];   // past the end of a shorter trace: state frozen, output 0, z = 1 saved
                 const float r = sigmoid_acc(px[0] + acc[rr][0] + bh[0]);
-                const float z = sigmoid_acc(px[1] + acc[rr][1] + bh[1]);
+                const float z = active ? sigmoid_acc(px[1] + acc[rr][1] + bh[1]) : 1.0f;
                 const float hn = acc[rr][2] + bh[2];
                 const float n = tanhf(px[2] + r * hn);
                 const float hold = hcur[rr * H + i];
-                const float hnew = (1.0f - z) * n + z * hold;
+                const float hnew = active ? (1.0f - z) * n + z * hold : hold;
                 hnxt[rr * H + i] = hnew;
-                out.at(b, t)[dir * H + i] = hnew;
+                out.at(b, t)[dir * H + i] = active ? hnew : 0.0f;
                 if (gates) {
                     float* gp = gates + ((((size_t)dir * B + b) * T + t) * 4) * H + i;
                     gp[0] = r; gp[H] = z; gp[2 * H] = n; gp[3 * H] = hn;
@@ -129,7 +133,7 @@ gru_fwd_f32_kernel(Seq x, int I, const float* __restrict__ w_ih, const float* __
 template <int R, bool WSMEM, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 gru_bwd_f32_kernel(Seq d_out, const float* __restrict__ d_h_n, const float* __restrict__ gates, Seq out,
-                   const float* __restrict__ w_hh, Seq dGx, Seq dGh, int B, int T, int H) {
+                   const float* __restrict__ w_hh, Seq dGx, Seq dGh, const int* __restrict__ lengths, int B, int T, int H) {
     extern __shared__ __align__(16) float smem_f[];
     const int i = threadIdx.x, y = threadIdx.y, S = blockDim.y, Bt = S * R;
     const int dir = blockIdx.y;
@@ -160,7 +164,7 @@ gru_bwd_f32_kernel(Seq d_out, const float* __restrict__ d_h_n, const float* __re
             direct[rr] = 0.0f;
             if (b < B) {
                 float d = dh[rr];
-                if (d_out.p) d += d_out.at(b, t)[dir * H + i];
+                if (d_out.p && (!lengths || t < lengths[b])) d += d_out.at(b, t)[dir * H + i];   // padded outputs carry no gradient
                 const float* gp = gates + ((((size_t)dir * B + b) * T + t) * 4) * H + i;
                 const float r = gp[0], z = gp[H], n = gp[2 * H], hn = gp[3 * H];
                 const float hprev = (step == 0) ? 0.0f : out.at(b, t_prev)[dir * H + i];
@@ -234,7 +238,7 @@ int set_smem(K kern, size_t bytes) {
 extern "C" int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int64_t x_row0, int I, const float* w_ih,
                               const float* b_ih, const float* P, int64_t p_ld, int64_t p_rows, int64_t p_row0,
                               const float* w_hh_t, const float* b_hh, float* out, int64_t o_ld, int64_t o_rows,
-                              int64_t o_row0, float* h_n, float* gates, int B, int T, int H, void* stream_) {
+                              int64_t o_row0, float* h_n, float* gates, const int* lengths, int B, int T, int H, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -257,7 +261,7 @@ extern "C" int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int6
     do {                                                                                                         \
         if (set_smem(gru_fwd_f32_kernel<RR, WS, MT>, smem)) return 2;                                            \
         gru_fwd_f32_kernel<RR, WS, MT><<<grid, block, smem, stream>>>(sx, I, w_ih, b_ih, sp, w_hh_t, b_hh, so,   \
-                                                                      h_n, gates, B, T, H);                      \
+                                                                      h_n, gates, lengths, B, T, H);             \
     } while (0)
 #define RS_PICK_FWD(RR)                                                                                          \
     do {                                                                                                         \
@@ -276,7 +280,7 @@ extern "C" int rs_gru_fwd_f32(const float* x, int64_t x_ld, int64_t x_rows, int6
 extern "C" int rs_gru_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows, int64_t do_row0, const float* d_h_n,
                               const float* gates, const float* out, int64_t o_ld, int64_t o_rows, int64_t o_row0,
                               const float* w_hh, float* dGx, float* dGh, int64_t g_ld, int64_t g_rows, int64_t g_row0,
-                              int B, int T, int H, void* stream_) {
+                              const int* lengths, int B, int T, int H, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -294,8 +298,8 @@ extern "C" int rs_gru_bwd_f32(const float* d_out, int64_t do_ld, int64_t do_rows
 #define RS_LAUNCH_BWD(RR, WS, MT)                                                                               \
     do {                                                                                                        \
         if (set_smem(gru_bwd_f32_kernel<RR, WS, MT>, smem)) return 2;                                           \
-        gru_bwd_f32_kernel<RR, WS, MT><<<grid, block, smem, stream>>>(sdo, d_h_n, gates, so, w_hh, sgx, sgh, B, \
-                                                                      T, H);                                    \
+        gru_bwd_f32_kernel<RR, WS, MT><<<grid, block, smem, stream>>>(sdo, d_h_n, gates, so, w_hh, sgx, sgh,    \
+                                                                      lengths, B, T, H);                        \
     } while (0)
 #define RS_PICK_BWD(RR)                                                                                         \
     do {                                                                                                        \

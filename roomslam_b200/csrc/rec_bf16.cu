@@ -39,6 +39,7 @@ struct FwdParams {
     uint8_t* out; long long out_block_bytes;     // tile-major, C = 2H
     uint8_t* gates;                         // [tiles][T][2][64][128][8] fp16 (private to fwd/bwd) or NULL
     float* h_n;                             // [2][B][H]
+    const int* lengths;                     // [B] valid steps per trace (packed-sequence semantics) or NULL
     int B, T;
     int pf_dist;                            // L2 prefetch distance in steps (0 = off)
 };
@@ -100,6 +101,7 @@ __device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
     return pack8(c);
 }
 
+template <bool kVarLen>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;                               // [16 chunks][384 rows][16 B]
@@ -202,9 +204,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
         uint8_t* a_row = a_s + row * 16;
         uint8_t* h32_row = h32_s + row * 16;
         const float* xrow = p.x ? p.x + b * T * p.I : nullptr;
+        const int len = (kVarLen && live) ? p.lengths[b] : T;      // steps past the end of a shorter trace: h frozen, out = 0
 
         for (int step = 0; step < T; ++step) {
             const int t = dir ? (T - 1 - step) : step;
+            const bool active = !kVarLen || t < len;              // compile-time true without lengths: the fast path is unchanged
             const long long blk = (long long)tile * (T + 2) + t + 1;
             const uint8_t* pblk = p.P ? p.P + blk * p.p_block_bytes + (long long)(dir * 48) * CHUNK + row * 16 : nullptr;
             uint8_t* oblk = p.out + blk * p.out_block_bytes + (long long)(dir * 16) * CHUNK + row * 16;
@@ -260,17 +264,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
                 for (int j = 0; j < 8; ++j) {
                     // the host folds the 1/2 of sigma(a) = 1/2 tanh(a/2) + 1/2 into the r and z rows of W_hh, W_ih and the biases
                     const float r = fmaf(0.5f, tanh_fast(gr_[j] + pr[j]), 0.5f);
-                    const float z = fmaf(0.5f, tanh_fast(gz_[j] + pz[j]), 0.5f);
+                    const float z = active ? fmaf(0.5f, tanh_fast(gz_[j] + pz[j]), 0.5f) : 1.0f;   // z = 1 saved: BPTT passes dh through
                     const float hn = gn_[j] + bhn_s[u0 + j];
                     const float n = tanh_fast(fmaf(r, hn, pn[j]));
-                    hv[j] = fmaf(z, ho[j] - n, n);
+                    hv[j] = active ? fmaf(z, ho[j] - n, n) : ho[j];
                     rv[j] = r; zv[j] = z; nv[j] = n; hnv[j] = hn;
                 }
                 *reinterpret_cast<float4*>(h32_row + (u0 / 4) * CHUNK) = make_float4(hv[0], hv[1], hv[2], hv[3]);
                 *reinterpret_cast<float4*>(h32_row + (u0 / 4 + 1) * CHUNK) = make_float4(hv[4], hv[5], hv[6], hv[7]);
                 const uint4 o0 = pack8(hv);
                 *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK) = o0;      // next step's A operand, in place
-                stg16(oblk + (long long)(u0 / 8) * CHUNK, o0);
+                stg16(oblk + (long long)(u0 / 8) * CHUNK, active ? o0 : make_uint4(0, 0, 0, 0));
                 if (gblk) {
                     stg16(gblk + (long long)(0 * 16 + u0 / 8) * CHUNK, pack8h(rv));
                     stg16(gblk + (long long)(1 * 16 + u0 / 8) * CHUNK, pack8h(zv));
@@ -303,10 +307,12 @@ struct BwdParams {
     const uint8_t* out; long long out_block_bytes;       // this layer's h (tile-major, C = 2H, zero pad rows)
     const uint8_t* WhhT;                                 // [2][48][128][8] bf16: rows = h index, K = (r | z | hn) gate rows
     uint8_t* dG; long long dg_block_bytes;               // tile-major C = 8H: [dir][r | z | n | hn][H]
+    const int* lengths;                                  // [B] or NULL
     int B, T;
     int pf_dist;
 };
 
+template <bool kVarLen>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;                               // [48 chunks][128 rows][16 B]
@@ -380,6 +386,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
         const bool live = b < p.B;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
         uint8_t* a_row = a_s + row * 16;
+        const int len = (kVarLen && live) ? p.lengths[b] : T;
         // the carry z (.) dh lives in the TMEM accumulator; it starts as d_h_n
 #pragma unroll
         for (int sc = 0; sc < 4; ++sc) {
@@ -431,6 +438,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
             const int fstep = T - 1 - s;
             const int t = dir ? (T - 1 - fstep) : fstep;
             const long long blk = (long long)tile * (T + 2) + t + 1;
+            const bool active = !kVarLen || t < len;        // padded outputs carry no gradient (their saved z is 1)
             uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 64) * CHUNK + row * 16;
             if (s > 0) {
                 rs::mbar_wait(acc_full, (s - 1) & 1);
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
                     float gr[8], gz[8], gn[8], ghn[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float dh = __uint_as_float(acc[hf * 8 + j]) + dout[j];
+                        const float dh = __uint_as_float(acc[hf * 8 + j]) + (active ? dout[j] : 0.0f);
                         const float dn = dh * (1.0f - z[j]);
                         const float dz = dh * (hp[j] - n[j]);
                         gn[j] = dn * (1.0f - n[j] * n[j]);
@@ -526,7 +534,8 @@ int pf_dist_env(const char* name, int dflt) {
 }  // namespace
 
 extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh,
-                               const float* b_hn, void* out, void* gates, float* h_n, int B, int T, void* stream_) {
+                               const float* b_hn, void* out, void* gates, float* h_n, const int* lengths, int B, int T,
+                               void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -543,18 +552,23 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
     p.P = static_cast<const uint8_t*>(P); p.p_block_bytes = 6LL * H * 256;
     p.Whh = static_cast<const uint8_t*>(Whh); p.b_hn = b_hn;
     p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
-    p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.B = B; p.T = T;
+    p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.lengths = lengths; p.B = B; p.T = T;
     p.pf_dist = pf_dist_env("RS_PF_DIST_FWD", 1);
     const int smem = W_BYTES + WX_BYTES + A_FWD_BYTES + H32_BYTES + H * 4 + 64;
-    RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rec_fwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    if (lengths) {
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        rec_fwd_bf16_kernel<true><<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    } else {
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        rec_fwd_bf16_kernel<false><<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    }
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT,
-                               void* dG, int B, int T, void* stream_) {
+                               void* dG, const int* lengths, int B, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -565,11 +579,17 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
     p.out = static_cast<const uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
     p.WhhT = static_cast<const uint8_t*>(WhhT);
     p.dG = static_cast<uint8_t*>(dG); p.dg_block_bytes = 8LL * H * 256;
+    p.lengths = lengths;
     p.B = B; p.T = T;
     p.pf_dist = pf_dist_env("RS_PF_DIST_BWD", 0);
     const int smem = W_BYTES + A_BWD_BYTES + 64;
-    RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rec_bwd_bf16_kernel<<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    if (lengths) {
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        rec_bwd_bf16_kernel<true><<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    } else {
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        rec_bwd_bf16_kernel<false><<<dim3((B + 127) / 128, 2), NUM_THREADS, smem, stream>>>(p);
+    }
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -169,7 +169,7 @@ class GRULayerFn(torch.autograd.Function):
 
     apply(xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         -> (out_padded (B, T+2, 2H), h_n (2, B, H))
-    meta = (padded_in, B, T).
+    meta = (padded_in, B, T[, lengths]); lengths: int32 (B,) valid steps per trace (packed-sequence semantics) or None.
     xin : padded_in False: the traces (B, T, I);  True: the padded output (B, T+2, I) of the layer below.
     mask: None or (B, T, I) dropout keep-mask (scaled by 1/(1-p)) applied to xin (decision D4).
     One Function per layer, so a layer's weight gradients are final (and can be all-reduced) while the
@@ -179,6 +179,7 @@ class GRULayerFn(torch.autograd.Function):
     def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         _need_cuda(xin, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         padded_in = meta[0]
+        lengths = meta[3] if len(meta) > 3 else None
         xin = xin.contiguous().float()
         ctx.padded_in_orig = bool(padded_in)
         B, Il = xin.shape[0], xin.shape[2]
@@ -206,7 +207,7 @@ class GRULayerFn(torch.autograd.Function):
             with ktime("gru_fwd_f32_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
                 _lib.call("rs_gru_fwd_f32", _p(xin), Il, xin.shape[1], 1 if padded_in else 0, Il, _p(w_ih_cat),
                           _p(b_ih_cat), 0, 0, 0, 0, _p(w_hh_t), _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n),
-                          _p(gates), B, T, H, st)
+                          _p(gates), _p(lengths), B, T, H, st)
         else:
             if not padded_in:
                 xp = padded(B, T, Il, dev)
@@ -224,10 +225,11 @@ class GRULayerFn(torch.autograd.Function):
                     linear_nt(xin.view(B * (T + 2), Il), w_ih_cat, b_ih_cat, P.view(B * (T + 2), 6 * H))
             with ktime("gru_fwd_f32_kernel", rec_flops):
                 _lib.call("rs_gru_fwd_f32", 0, 0, 0, 0, Il, 0, _p(b_ih_cat), _p(P), 6 * H, T + 2, 1, _p(w_hh_t),
-                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n), _p(gates), B, T, H, st)
+                          _p(b_hh_cat), _p(out), 2 * H, T + 2, 1, _p(h_n), _p(gates), _p(lengths), B, T, H, st)
             del P
         ctx.dims = (B, T, Il, H)
         ctx.mask = mask
+        ctx.lengths = lengths
         ctx.padded_in_saved = bool(padded_in)
         ctx.save_for_backward(out, gates, xin, w_ih_cat, w_hh_cat)   # outputs must go through save_for_backward (no ref cycle)
         return out, h_n
@@ -249,7 +251,7 @@ class GRULayerFn(torch.autograd.Function):
         dGh = padded(B, T, 6 * H, dev)
         with ktime("gru_bwd_f32_kernel", 2.0 * B * T * 2 * 3 * H * H):
             _lib.call("rs_gru_bwd_f32", _p(d_out), 2 * H, Tp, 1, _p(d_h_n), _p(gates), _p(out), 2 * H, Tp, 1,
-                      _p(w_hh_cat), _p(dGx), _p(dGh), 6 * H, Tp, 1, B, T, H, st)
+                      _p(w_hh_cat), _p(dGx), _p(dGh), 6 * H, Tp, 1, _p(ctx.lengths), B, T, H, st)
         dGx2, dGh2, out2 = dGx.view(M, 6 * H), dGh.view(M, 6 * H), out.view(M, 2 * H)
         if not padded_in:                                # layer 0 with the fused projection: x is not padded
             xp = padded(B, T, Il, dev)
@@ -308,14 +310,17 @@ class GRULayerFn(torch.autograd.Function):
                 dW_ih[3 * H:], dW_hh[1], db_ih[3 * H:], db_hh[3 * H:])
 
 
-def gru_encoder(x, mask, num_layers, weights, layer_fn=None):
-    """Stack of bidirectional layers -> (out (B,T,2H) of the top layer, h_n (2L,B,H)), torch.nn.GRU semantics."""
+def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None):
+    """Stack of bidirectional layers -> (out (B,T,2H) of the top layer, h_n (2L,B,H)), torch.nn.GRU semantics
+    (with `lengths`: those of a packed sequence)."""
     layer_fn = layer_fn or GRULayerFn
     B, T = x.shape[0], x.shape[1]
     cur, padded_in, h_all = x, False, []
+    if lengths is not None:
+        lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
     for l in range(num_layers):
         m = mask[l - 1] if (mask is not None and l > 0) else None
-        cur, h_n = layer_fn.apply(cur, (padded_in, B, T), m, *weights[8 * l: 8 * l + 8])
+        cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths), m, *weights[8 * l: 8 * l + 8])
         padded_in = True
         h_all.append(h_n)
     h_n = torch.cat(h_all, 0) if num_layers > 1 else h_all[0]

@@ -80,7 +80,8 @@ class GRULayerBF16Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         _need_cuda(xin, mask, w_ih, w_hh)
-        padded_in, B, T = meta
+        padded_in, B, T = meta[:3]
+        lengths = meta[3] if len(meta) > 3 else None
         if w_hh.shape[1] != H:
             raise _lib.RoomSlamError(f"bf16 mode is built for hidden_size = {H} (got {w_hh.shape[1]}); use precision='fp32'")
         dev = xin.device
@@ -125,7 +126,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 xcols[:, :, 7] = bias_x - b_hi
                 whh_img = torch.cat([whh_img, xcols.to(torch.bfloat16).view(2, 3 * H, 2, 8).permute(0, 2, 1, 3)], 1).contiguous()
                 with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
-                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), B, T, st)
+                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths), B, T, st)
                 saved_in = x
             else:
                 X = xin
@@ -137,11 +138,12 @@ class GRULayerBF16Fn(torch.autograd.Function):
                     _nt(X, Il, [8 * k for k in range(Il // 64)], wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
                 with ktime("rec_fwd_bf16_kernel", rec_flops):
-                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), B, T, st)
+                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths), B, T, st)
                 del P
                 saved_in = X
         ctx.meta = (padded_in, B, T, Il)
         ctx.mask = mask
+        ctx.lengths = lengths
         # save_for_backward (not ctx attributes): `out` is an OUTPUT of this node; holding it in a plain attribute
         # would create a reference cycle node -> out -> grad_fn -> node and keep gigabytes alive until the cycle GC runs
         ctx.save_for_backward(out, gates, saved_in, w_ih_cat, w_hh_cat)
@@ -165,7 +167,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
             dG[:, 0].zero_()
             dG[:, T + 1].zero_()
             with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
-                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), B, T, st)
+                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths), B, T, st)
             # ALL weight / bias gradients of the layer in one fused pass over dG (12 roles, see csrc/gemm_blk.cu):
             #   ih roles (dir, g in r,z,n): dG block ^T . X            -> dW_ih rows, bias sums of r, z, n
             #   hh roles (dir, g in r,z,hn): dG block ^T . h(t' -/+ 1) -> dW_hh rows, bias sum of hn

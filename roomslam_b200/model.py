@@ -111,33 +111,45 @@ class RoomSLAM(nn.Module):
             raise _lib.RoomSlamError("RoomSLAM runs on CUDA (sm_100a) only: move the model and inputs to the GPU; "
                                      "there is no CPU fallback")
 
-    def encode(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None):
-        """(out (B,T,2H) of the top layer, h_n (2L,B,H)) with torch.nn.GRU semantics."""
+    def _check_lengths(self, x, lengths):
+        if lengths is None:
+            return None
+        lengths = torch.as_tensor(lengths)
+        if lengths.shape != (x.shape[0],) or (x.shape[0] and (int(lengths.min()) < 1 or int(lengths.max()) > x.shape[1])):
+            raise ValueError("lengths must hold one value in [1, T] per trace (torch.nn.utils.rnn.pack_padded_sequence's rule)")
+        return lengths
+
+    def encode(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None):
+        """(out (B,T,2H) of the top layer, h_n (2L,B,H)) with torch.nn.GRU semantics; with `lengths` (valid steps per
+        trace) those of a packed sequence: zero outputs past a trace's end, h_n taken at its last valid step."""
         self._check_input(x)
+        lengths = self._check_lengths(x, lengths)
         if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
             dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
         if dropout_mask is not None:
             if dropout_mask.dim() == 3:
                 dropout_mask = dropout_mask.unsqueeze(0)
             dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
-        out, h_n = self._encode(x, dropout_mask)
+        out, h_n = self._encode(x, dropout_mask, lengths)
         if isinstance(out, F_._LazyOut):
             out = out.materialize()
         return out, h_n
 
-    def _encode(self, x, dropout_mask):
+    def _encode(self, x, dropout_mask, lengths=None):
         layer_fn = F_.GRULayerFn if self.precision == "fp32" else _bf16_layer_fn()
-        return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn)
+        return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn, lengths)
 
-    def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
+                lengths: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self._check_input(x)
+        lengths = self._check_lengths(x, lengths)
         if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
             dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
         if dropout_mask is not None:
             if dropout_mask.dim() == 3:
                 dropout_mask = dropout_mask.unsqueeze(0)
             dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
-        _, h_n = self._encode(x, dropout_mask)
+        _, h_n = self._encode(x, dropout_mask, lengths)
         latent = torch.cat([h_n[-2], h_n[-1]], dim=-1)          # decision D5 (README.md:115)
         return self.decoder(latent)
 
