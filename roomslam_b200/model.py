@@ -83,8 +83,8 @@ class RoomSLAM(nn.Module):
     def __init__(self, input_size: int = 2, hidden_size: int = 128, num_layers: int = 2, max_objects: int = 10,
                  num_classes: int = 4, dropout: float = 0.1, decoder_hidden: int = 256, precision: str = "fp32"):
         super().__init__()
-        if precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        if precision not in ("fp32", "bf16", "auto"):
+            raise ValueError(f"precision must be 'fp32', 'bf16' or 'auto', got {precision!r}")
         if hidden_size % 32 or not (32 <= hidden_size <= 512):
             raise ValueError("hidden_size must be a multiple of 32 in [32, 512]")
         self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
@@ -135,8 +135,19 @@ class RoomSLAM(nn.Module):
             out = out.materialize()
         return out, h_n
 
+    AUTO_BF16_MIN_BATCH = 256
+
+    def _use_bf16(self, batch: int) -> bool:
+        """'auto': the tensor-core bf16 kernels from 256 traces per step (where their 2e-2 gradient bar holds)
+        when the shape fits them (H = 128, at most 2 input columns); the fp32 kernels (1e-4) otherwise."""
+        if self.precision == "auto":
+            return batch >= self.AUTO_BF16_MIN_BATCH and self.hidden_size == 128 and self.input_size <= 2
+        return self.precision == "bf16"
+
     def _encode(self, x, dropout_mask, lengths=None):
-        layer_fn = F_.GRULayerFn if self.precision == "fp32" else _bf16_layer_fn()
+        bf16 = self._use_bf16(x.shape[0])
+        self.decoder.precision = "bf16" if bf16 else "fp32"
+        layer_fn = _bf16_layer_fn() if bf16 else F_.GRULayerFn
         return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn, lengths)
 
     def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
