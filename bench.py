@@ -535,7 +535,7 @@ def run_next_rows(args):
 
 # DRAM bytes per launch of the training step's kernels at the benchmark shape (8192 traces x 500 steps per GPU, bf16), from
 # `ncu --set full` captures of tools/step_once.py 8192 (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_step_kernels_ncu.md)
-NCU_TRAFFIC_B8192 = {"rec_bwd_bf16_kernel": 20.947e9}
+NCU_TRAFFIC_B8192 = {"rec_bwd_bf16_kernel": 20.947e9, "blk_wgrad_kernel": (16.472e9 + 12.712e9) / 2}
 
 
 def train_roofline(kernel_ms, B, pk, precision):
