@@ -13,7 +13,8 @@
 //   (np.linspace(0, N-1, max_len, dtype=int)); an empty trace yields one zero row.
 // Every operation is an explicit round-to-nearest intrinsic and the file is compiled with -fmad=false: the result is
 // bit-identical to the numpy reference.  One thread per output row (a row needs the three source points i-2 .. i,
-// served by L1), rows staged in shared memory and written back as contiguous 16-byte stores.
+// served by L1); each warp stages its 32 rows in shared memory and writes them back as contiguous 16-byte stores
+// (warp-level synchronisation only).
 #include "common.cuh"
 #include "../../include/roomslam_b200.h"
 
@@ -38,11 +39,13 @@ __global__ void __launch_bounds__(256)
 trace_features_kernel(const float4* __restrict__ pts, const long long* __restrict__ offsets, int B, int max_len, int out_len,
                       float* __restrict__ feats, unsigned char* __restrict__ mask, long long* __restrict__ lengths,
                       int* __restrict__ unsorted_flag, int vec_ok) {
-    __shared__ __align__(16) float rows[256 * 11];               // one chunk of 256 output rows, stored coalesced below
+    __shared__ __align__(16) float rows_all[256 * 11];           // per warp: 32 output rows (1408 B), stored coalesced below
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rows = rows_all + warp * 32 * 11;
     const long long total = (long long)B * out_len;
-    const long long chunks = (total + 255) / 256;
-    for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
-        const long long e = c * 256 + threadIdx.x;
+    const long long groups = (total + 31) / 32;                  // one warp per group of 32 consecutive output rows
+    for (long long gidx = (long long)blockIdx.x * 8 + warp; gidx < groups; gidx += (long long)gridDim.x * 8) {
+        const long long e = gidx * 32 + lane;
         if (e < total) {
             const int b = (int)(e / out_len), j = (int)(e % out_len);
             const long long o0 = offsets[b];
@@ -79,24 +82,23 @@ trace_features_kernel(const float4* __restrict__ pts, const long long* __restric
                 row[10] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
             }
 #pragma unroll
-            for (int k = 0; k < 11; ++k) rows[threadIdx.x * 11 + k] = row[k];    // stride 11 words: conflict-free
+            for (int k = 0; k < 11; ++k) rows[lane * 11 + k] = row[k];           // stride 11 words: conflict-free
             mask[e] = valid ? 1 : 0;
         }
-        __syncthreads();
-        const long long nrows = (total - c * 256 < 256) ? (total - c * 256) : 256;
+        __syncwarp();
+        const long long nrows = (total - gidx * 32 < 32) ? (total - gidx * 32) : 32;
         const int nfl = (int)nrows * 11;
-        float* dst = feats + c * 256 * 11;                       // 256 * 44 B per chunk: 16-byte aligned when feats is
+        float* dst = feats + gidx * 32 * 11;                     // 32 * 44 B per group: 16-byte aligned when feats is
         if (vec_ok) {
-            for (int q = threadIdx.x; q < nfl / 4; q += 256)
+            for (int q = lane; q < nfl / 4; q += 32)
                 reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(rows)[q];
-            for (int q = (nfl & ~3) + threadIdx.x; q < nfl; q += 256) dst[q] = rows[q];
+            for (int q = (nfl & ~3) + lane; q < nfl; q += 32) dst[q] = rows[q];
         } else {
-            for (int q = threadIdx.x; q < nfl; q += 256) dst[q] = rows[q];
+            for (int q = lane; q < nfl; q += 32) dst[q] = rows[q];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
-
 
 // ---- uniform-rate resampling + windowing for the GRU input (decision D14: README.md:145 "10 Hz", windows of seq_len) ----
 // One thread per output sample: t_i of numpy's arange(t_first, t_last, 1/hz) (element 0 = start, 1 = start + step,
