@@ -177,6 +177,9 @@ class GRULayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        # unused outputs (the top layer's sequence output feeds nothing: only h_n reaches the decoder) must arrive in
+        # backward as None, not as a materialised 2 GB tensor of zeros that is then filled, converted and read back
+        ctx.set_materialize_grads(False)
         _need_cuda(xin, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         padded_in = meta[0]
         lengths = meta[3] if len(meta) > 3 else None
