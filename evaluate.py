@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--checkpoint", default="checkpoints/best_model.pth")
     ap.add_argument("--data_dir", default="data/sample")
     ap.add_argument("--compare_baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "auto"])
     args = ap.parse_args()
     x, tgt = data.load_dir(args.data_dir)
     model = RoomSLAM(precision=args.precision).cuda().eval()

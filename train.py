@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=NUM_EPOCHS)
     ap.add_argument("--batch_size", type=int, default=BATCH_SIZE)
     ap.add_argument("--lr", type=float, default=LEARNING_RATE)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "auto"])
     ap.add_argument("--create_sample_data", action="store_true")
     ap.add_argument("--checkpoint_dir", default="checkpoints")
     ap.add_argument("--seed", type=int, default=0)
