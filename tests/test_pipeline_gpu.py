@@ -85,3 +85,31 @@ def test_real_traces_and_real_colliders_overfit():
     loader = [{"traces": x.cpu(), "trace_mask": mask.cpu(), **{k: v.cpu() for k, v in targets.items()}}]
     m = evaluate_metrics(model, loader, "cuda")
     assert m["tp"] + m["fp"] == 33 and m["fn"] == 0 and m["cls_acc"] > 0.5
+
+
+def test_train_benchmark_driver_on_files(tmp_path):
+    """train_benchmark.py end to end on trace / collider JSON files in the upstream dataset format."""
+    import json
+    import os
+    import subprocess
+    import sys
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    f = np.load(os.path.join(gdir, "features.npz"))
+    cols = json.loads(str(np.load(os.path.join(gdir, "colliders.npz"))["train_json"]))
+    for split, ks in (("train", (0, 1)), ("val", (2,))):
+        d = tmp_path / split
+        d.mkdir()
+        json.dump({"colliders": cols}, open(d / "colliders.json", "w"))
+        for k in ks:
+            pts = f[f"real{k}_points"][:900]
+            json.dump([{"timestamp": float(p[3]), "x": float(p[0]), "y": float(p[1]), "z": float(p[2])} for p in pts],
+                      open(d / f"human_data_{k}.json", "w"))
+    root = os.path.dirname(os.path.dirname(__file__))
+    out = subprocess.run([sys.executable, os.path.join(root, "train_benchmark.py"), "--data_dir", str(tmp_path / "train"),
+                          "--val_dir", str(tmp_path / "val"), "--save_dir", str(tmp_path / "ckpt"), "--epochs", "3",
+                          "--max_trace_len", "600"], capture_output=True, text=True, cwd=root, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Epoch 2:" in out.stdout and "Training completed!" in out.stdout
+    ck = torch.load(tmp_path / "ckpt" / "best_model.pth", map_location="cpu", weights_only=False)
+    assert {"epoch", "model_state_dict", "optimizer_state_dict", "val_loss", "metrics", "config"} <= set(ck)
+    assert "encoder.lstm.weight_hh_l1_reverse" in ck["model_state_dict"] and ck["config"]["model_type"] == "lstm"
