@@ -113,3 +113,12 @@ def test_train_benchmark_driver_on_files(tmp_path):
     ck = torch.load(tmp_path / "ckpt" / "best_model.pth", map_location="cpu", weights_only=False)
     assert {"epoch", "model_state_dict", "optimizer_state_dict", "val_loss", "metrics", "config"} <= set(ck)
     assert "encoder.lstm.weight_hh_l1_reverse" in ck["model_state_dict"] and ck["config"]["model_type"] == "lstm"
+    # the shipped inference CLI on that checkpoint (threshold 0 keeps every query that survives NMS)
+    res = tmp_path / "pred.json"
+    out = subprocess.run([sys.executable, os.path.join(root, "inference_benchmark.py"), "--checkpoint", str(tmp_path / "ckpt" / "best_model.pth"),
+                          "--input", str(tmp_path / "val" / "human_data_2.json"), "--output", str(res), "--threshold", "0.0"],
+                         capture_output=True, text=True, cwd=root, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    pred = json.load(open(res))
+    assert pred["metadata"]["num_colliders"] == len(pred["colliders"]) >= 1
+    assert set(pred["colliders"][0]) == {"type", "label", "confidence", "center", "size", "radius", "height"}
