@@ -116,6 +116,13 @@ int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, 
 int rs_split_bf16x6(const float* x, int64_t ld, int64_t rows, int cols, int kpad, int role_b, void* out, int64_t ld_out,
                     void* stream);
 
+/* The same with the reduction running over n_seg (<= 8) passes of the same rows, pass s reading the column blocks
+ * a_col0 + a_seg[s] of A and b_col0 + b_seg[s] of B (host int arrays): all partial products of a split-operand ("bf16x6")
+ * weight gradient in ONE launch. */
+int rs_gemm_bf16_tn_seg_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift, const void* B,
+                            int64_t ldb, int64_t b_rows, int b_col0, int b_row_shift, int n_seg, const int* a_seg,
+                            const int* b_seg, float* C, int64_t ldc, int M, int N, int64_t rows, void* stream);
+
 /* ---- optimizer: global-norm clipping + AdamW over one flat fp32 buffer (upstream train.py:220, :440-444) ------- */
 /* g is first scaled by grad_scale (1/world_size after a sum all-reduce), then clipped to max_norm (<= 0: off). */
 int rs_adamw_step_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -34,6 +34,8 @@ struct GemmParams {
     int k_rows_per_split;   // TN: rows per split (multiple of BK)
     int a_row_shift, b_row_shift;   // TN: row offsets applied to the TMA coordinates of A and B
     int a_col0, b_col0;     // TN: column offsets inside the global matrices (select a column block)
+    int n_seg, kb_per_seg;  // TN: the reduction runs over n_seg passes of the same rows with different column blocks
+    int a_seg[8], b_seg[8]; // TN: extra column offset of A / B in pass s (split-operand GEMMs: one launch for all partial products)
     const float* bias;      // NT: optional
     int flags;              // NT: RS_GEMM_RELU, RS_GEMM_OUT_F32
     float* c_nt_f32; long long ldc_nt;   // NT with fp32 output: direct row stores
@@ -97,14 +99,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         rs::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                         rs::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
                     } else {
-                        const int krow = split * p.k_rows_per_split + kb * BK;
-                        // MN-major operands: box = 64 columns (128 B) x 64 rows; two boxes cover 128 columns
-                        rs::tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_col0 + m_blk * BM, krow + p.a_row_shift);
-                        rs::tma_load_2d(sa + TILE_A_BYTES / 2, &tmap_a, &full_bar[stage], p.a_col0 + m_blk * BM + 64,
-                                        krow + p.a_row_shift);
-                        rs::tma_load_2d(sb, &tmap_b, &full_bar[stage], p.b_col0 + n_blk * BN, krow + p.b_row_shift);
-                        rs::tma_load_2d(sb + TILE_B_BYTES / 2, &tmap_b, &full_bar[stage], p.b_col0 + n_blk * BN + 64,
-                                        krow + p.b_row_shift);
+                        const int g = split * p.k_blocks + kb;              // k block over all passes
+                        const int seg = g / p.kb_per_seg;
+                        if (seg >= p.n_seg) {                                // tail of the last split: nothing left, feed zeros
+                            rs::tma_load_2d(sa, &tmap_a, &full_bar[stage], 0, 0x3fffffff);
+                            rs::tma_load_2d(sa + TILE_A_BYTES / 2, &tmap_a, &full_bar[stage], 0, 0x3fffffff);
+                            rs::tma_load_2d(sb, &tmap_b, &full_bar[stage], 0, 0x3fffffff);
+                            rs::tma_load_2d(sb + TILE_B_BYTES / 2, &tmap_b, &full_bar[stage], 0, 0x3fffffff);
+                        } else {
+                            const int krow = (g - seg * p.kb_per_seg) * BK;
+                            const int ac = p.a_col0 + p.a_seg[seg] + m_blk * BM, bc = p.b_col0 + p.b_seg[seg] + n_blk * BN;
+                            // MN-major operands: box = 64 columns (128 B) x 64 rows; two boxes cover 128 columns
+                            rs::tma_load_2d(sa, &tmap_a, &full_bar[stage], ac, krow + p.a_row_shift);
+                            rs::tma_load_2d(sa + TILE_A_BYTES / 2, &tmap_a, &full_bar[stage], ac + 64, krow + p.a_row_shift);
+                            rs::tma_load_2d(sb, &tmap_b, &full_bar[stage], bc, krow + p.b_row_shift);
+                            rs::tma_load_2d(sb + TILE_B_BYTES / 2, &tmap_b, &full_bar[stage], bc + 64, krow + p.b_row_shift);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -297,18 +307,18 @@ extern "C" int rs_gemm_bf16_nt(const void* A, int64_t lda, const void* B, int64_
     return 0;
 }
 
-// C[M,N] (fp32, ldc) += A[rows, a_col0 : a_col0+M]^T . B[rows, b_col0 : b_col0+N], pairing row r + a_row_shift of A
-// with row r + b_row_shift of B for r in [0, rows).  Rows outside the matrices read as zero.  M % 128 == 0, N % 128 == 0.
-extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift,
-                                   const void* B, int64_t ldb, int64_t b_rows, int b_col0, int b_row_shift, float* C,
-                                   int64_t ldc, int M, int N, int64_t rows, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (rs::check_device_sm100()) return 3;
-    if (rows == 0) return 0;        // nothing to do: empty tensors carry null pointers
+// C[M,N] (fp32, ldc) += sum over passes s < n_seg of  A[rows, a_col0 + a_seg[s] : +M]^T . B[rows, b_col0 + b_seg[s] : +N],
+// pairing row r + a_row_shift of A with row r + b_row_shift of B for r in [0, rows).  Rows outside the matrices read as
+// zero.  M % 128 == 0, N % 128 == 0.
+static int tn_launch(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift, const void* B, int64_t ldb,
+                     int64_t b_rows, int b_col0, int b_row_shift, int n_seg, const int* a_seg, const int* b_seg, float* C,
+                     int64_t ldc, int M, int N, int64_t rows, cudaStream_t stream) {
     RS_REQUIRE(A && B && C && M > 0 && N > 0 && rows >= 0, "rs_gemm_bf16_tn_acc: bad arguments");
     RS_REQUIRE(M % BM == 0 && N % BN == 0, "rs_gemm_bf16_tn_acc: need M %% 128 == 0 and N %% 128 == 0 (got %d x %d)", M, N);
     RS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "rs_gemm_bf16_tn_acc: leading dimensions must be multiples of 8");
     RS_REQUIRE(rows < (1ll << 31) && a_rows < (1ll << 31) && b_rows < (1ll << 31), "rs_gemm_bf16_tn_acc: too many rows");
+    RS_REQUIRE(n_seg >= 1 && n_seg <= 8, "rs_gemm_bf16_tn_acc: 1 <= passes <= 8");
+    if (rows == 0) return 0;
     CUtensorMap ta, tb;
     // clamp the visible rows so that nothing past the last valid pair is read (TMA returns zero out of bounds)
     const int64_t a_vis = (rows + a_row_shift < a_rows) ? rows + a_row_shift : a_rows;
@@ -321,7 +331,8 @@ extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, i
     p.m_tiles = M / BM;
     p.n_tiles = N / BN;
     const int out_tiles = p.m_tiles * p.n_tiles;
-    const long long kblocks_total = (rows + BK - 1) / BK;
+    const long long kb_per_seg = (rows + BK - 1) / BK;
+    const long long kblocks_total = kb_per_seg * n_seg;
     int splits = num_sms() / out_tiles;
     if (splits < 1) splits = 1;
     if (splits > kblocks_total) splits = (int)kblocks_total;
@@ -330,6 +341,8 @@ extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, i
     p.splits = splits;
     p.k_blocks = (int)kb_per_split;
     p.k_rows_per_split = (int)(kb_per_split * BK);
+    p.n_seg = n_seg; p.kb_per_seg = (int)kb_per_seg;
+    for (int s = 0; s < n_seg; ++s) { p.a_seg[s] = a_seg ? a_seg[s] : 0; p.b_seg[s] = b_seg ? b_seg[s] : 0; }
     p.a_row_shift = a_row_shift; p.b_row_shift = b_row_shift;
     p.a_col0 = a_col0; p.b_col0 = b_col0;
     p.c_f32 = C; p.ldc = ldc;
@@ -340,4 +353,21 @@ extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, i
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int rs_gemm_bf16_tn_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift,
+                                   const void* B, int64_t ldb, int64_t b_rows, int b_col0, int b_row_shift, float* C,
+                                   int64_t ldc, int M, int N, int64_t rows, void* stream_) {
+    if (rs::check_device_sm100()) return 3;
+    return tn_launch(A, lda, a_rows, a_col0, a_row_shift, B, ldb, b_rows, b_col0, b_row_shift, 1, nullptr, nullptr, C, ldc, M, N,
+                     rows, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int rs_gemm_bf16_tn_seg_acc(const void* A, int64_t lda, int64_t a_rows, int a_col0, int a_row_shift, const void* B,
+                                       int64_t ldb, int64_t b_rows, int b_col0, int b_row_shift, int n_seg, const int* a_seg,
+                                       const int* b_seg, float* C, int64_t ldc, int M, int N, int64_t rows, void* stream_) {
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(a_seg && b_seg, "rs_gemm_bf16_tn_seg_acc: null pointer");
+    return tn_launch(A, lda, a_rows, a_col0, a_row_shift, B, ldb, b_rows, b_col0, b_row_shift, n_seg, a_seg, b_seg, C, ldc, M, N,
+                     rows, static_cast<cudaStream_t>(stream_));
 }

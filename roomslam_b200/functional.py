@@ -147,9 +147,11 @@ def tn_tc(a3, kpa, a_col0, m_out, b3, kpb, n_out, out, a_shift=0, b_shift=0):
     """out[m_out, n_out] (fp32, zero-initialised by the caller) += A[:, a_col0:a_col0+m_out]^T . B[:, :n_out], row r + a_shift
     of A paired with row r + b_shift of B; both operands in the A-role split layout."""
     rows = a3.shape[0] - max(a_shift, b_shift)
-    for ta, tb in ((_LO, _HI), (_HI, _LO), (_MID, _MID), (_MID, _HI), (_HI, _MID), (_HI, _HI)):
-        _lib.call("rs_gemm_bf16_tn_acc", _p(a3), a3.stride(0), a3.shape[0], ta * kpa + a_col0, a_shift, _p(b3), b3.stride(0),
-                  b3.shape[0], tb * kpb, b_shift, _p(out), out.stride(0), m_out, n_out, rows, _stream(out))
+    order = ((_LO, _HI), (_HI, _LO), (_MID, _MID), (_MID, _HI), (_HI, _MID), (_HI, _HI))      # smallest products first
+    a_seg = (ctypes.c_int * 6)(*[ta * kpa for ta, _ in order])
+    b_seg = (ctypes.c_int * 6)(*[tb * kpb for _, tb in order])
+    _lib.call("rs_gemm_bf16_tn_seg_acc", _p(a3), a3.stride(0), a3.shape[0], a_col0, a_shift, _p(b3), b3.stride(0), b3.shape[0], 0,
+              b_shift, 6, ctypes.addressof(a_seg), ctypes.addressof(b_seg), _p(out), out.stride(0), m_out, n_out, rows, _stream(out))
 
 
 def _tc_ok(rows: int, *dims128) -> bool:
