@@ -60,3 +60,28 @@ def test_bf16_rejects_other_hidden_sizes():
     dev = RoomSLAM(hidden_size=64, precision="bf16").cuda()
     with pytest.raises(_lib.RoomSlamError):
         dev(torch.zeros(2, 4, 2, device="cuda"))
+
+
+def test_c1_shape_against_oracle_at_the_same_bf16_weights():
+    """BASELINE config 1 (32 traces x 500 steps) in bf16 mode.  Rounding the GRU weights to bf16 by itself moves the fp32
+    oracle's gradients by 2.3 % at this shape (tools/bf16_attrib_probe.py) -- the network, not the kernels.  Against the
+    oracle evaluated at the SAME bf16-rounded weights every gradient tensor is within the 2e-2 bar."""
+    import torch
+    from oracle.room_slam_ref import RoomSLAM as Ref
+    from roomslam_b200 import RoomSLAM, synth
+    torch.manual_seed(0)
+    ref = Ref(hidden_size=128, dropout=0.0).train()
+    dev = RoomSLAM(hidden_size=128, dropout=0.0, precision="bf16")
+    dev.load_state_dict(ref.state_dict())
+    dev = dev.cuda().train()
+    ref.load_state_dict({k: (v.bfloat16().float() if k.startswith("encoder.weight") else v) for k, v in ref.state_dict().items()})
+    x, tgt = synth.make_sample(32, 500, 10, seed=3)
+    lr = ref.compute_loss(ref(x), tgt)["total"]
+    lr.backward()
+    ld = dev.compute_loss(dev(x.cuda()), {k: v.cuda() for k, v in tgt.items()})["total"]
+    ld.backward()
+    assert abs(float(ld.detach()) - float(lr.detach())) < 2e-2 * abs(float(lr.detach()))
+    g = dict(ref.named_parameters())
+    for k, p in dev.named_parameters():
+        err = float((p.grad.double().cpu() - g[k].grad.double()).norm() / g[k].grad.double().norm().clamp_min(1e-12))
+        assert err < 2e-2, (k, err)
