@@ -42,3 +42,12 @@ def test_no_cpu_fallback_without_gpu(built_lib):
     with pytest.raises(_lib.RoomSlamError):
         b.heatmap(torch.zeros(2, 4, 2))
     assert _lib.load().rs_device_ok() == 0
+
+
+def test_every_symbol_is_documented_in_integration_md():
+    """INTEGRATION.md maps every exported entry point to the upstream interface it replaces."""
+    import os
+    from roomslam_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "INTEGRATION.md")).read()
+    missing = [name for name in _lib.parse_header() if name not in text]
+    assert not missing, missing
