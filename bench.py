@@ -2,9 +2,13 @@
 """Benchmark contract:  python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 Headline metric (BASELINE.json): training traces/s of the RoomSLAM bi-GRU (seq 500, H 128, 2 layers, N=10 objects)
-at batch 8192 per GPU, plus the occupancy-heatmap binning throughput in Gpoints/s (1M traces x 500 points, 0.05 m grid).
+at a GLOBAL batch of 8192 traces (BASELINE config 3: "global batch 8192, bf16, at 1/2/4/8 B200"), plus the
+occupancy-heatmap binning throughput in Gpoints/s (1M traces x 500 points in total, 0.05 m grid; config 2).
 One "step" = forward + multi-task loss + backward (+ NCCL gradient all-reduce for N > 1) + clip + AdamW on one
-synthetic batch.  Weak scaling: the per-GPU batch is fixed, the global batch grows with N.
+synthetic batch.  The headline `value` is STRONG scaling: the global batch is fixed and each of the N GPUs gets 8192/N
+traces; the weak-scaling figure (8192 traces PER GPU) is measured in the same run and reported under `weak`.
+`--scaling weak` swaps the two.  For N > 1 the run ends with an invariance check: the all-reduced gradients and the
+reduced heatmap grids of the N shards against one GPU processing the concatenated batch.
 
 Prints ONE JSON line (rank 0).  `value` is measured with the batch already resident in HBM; `e2e` repeats the
 measurement through the public API with HOST (pinned) inputs: host->device copies and the device->host read of the
@@ -29,8 +33,8 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 SEQ_LEN, HIDDEN, LAYERS, MAX_OBJECTS = 500, 128, 2, 10
-TRAIN_BATCH = 8192                     # per GPU (BASELINE config 3)
-HEATMAP_TRACES = 1_000_000             # per GPU (BASELINE config 2)
+TRAIN_BATCH = 8192                     # GLOBAL batch (BASELINE config 3); per GPU in the weak-scaling leg
+HEATMAP_TRACES = 1_000_000             # in total (BASELINE config 2); per GPU in the weak-scaling leg
 METRIC = "train traces/sec (seq500, H128) at 1/2/4/8 B200; heatmap Gpoints/s"
 
 
@@ -97,17 +101,24 @@ def cpu_heatmap_baseline(reps: int = 3, sample_traces: int = 40_000):
 
 
 def run_reference(args):
+    """The CPU reference arm: K timed + W warm-up steps of the oracle, each on a bounded sample (32 traces = BASELINE
+    config 1) of the workload; `steps`, `warmup` and `ms_per_step` describe exactly what was timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb = cpu_train_baseline(max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    sample_batch = 32
+    cb = cpu_train_baseline(args.steps, args.warmup, sample_batch)
     hb = cpu_heatmap_baseline()
+    cfg = workload_config(args, precision="fp32", world=args.gpus)
+    cfg["reference_sample"] = {"traces_per_step": sample_batch, "steps_timed": args.steps, "warmup_steps": args.warmup,
+                               "note": "each step = one bounded sample of the workload (BASELINE config 1 batch), "
+                                       "fwd+loss+bwd+clip+AdamW in fp32 on all host cores"}
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "traces/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, precision="fp32"),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "traces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "heatmap": {"value": hb["value"], "unit": "Gpoints/s", "cpu_baseline": hb,
@@ -117,13 +128,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, precision):
+def shard_sizes(args, world):
+    """(train traces per GPU, heatmap traces per GPU) of the headline leg."""
+    if args.scaling == "strong":
+        if args.batch % world or args.heatmap_traces % world:
+            raise SystemExit(f"--scaling strong: batch {args.batch} and heatmap traces {args.heatmap_traces} must divide by {world} GPUs")
+        return args.batch // world, args.heatmap_traces // world
+    return args.batch, args.heatmap_traces
+
+
+def workload_config(args, precision, world):
+    b_gpu, h_gpu = shard_sizes(args, world)
     return {"workload": f"RoomSLAM bi-GRU H={HIDDEN} L={LAYERS} seq_len={SEQ_LEN} N={MAX_OBJECTS}, fwd+loss+bwd+clip+AdamW, "
-                        f"batch {args.batch}/GPU (global {args.batch * args.gpus}); heatmap: {args.heatmap_traces} traces x "
-                        f"{SEQ_LEN} points/GPU, 10 m x 10 m room, 0.05 m grid",
-            "global_batch": args.batch * args.gpus, "seq_len": SEQ_LEN, "hidden": HIDDEN, "layers": LAYERS,
-            "precision": precision, "parallelism": f"dp{args.gpus}",
-            "l2": "inputs larger than L2 (train activations are GBs per step; heatmap input 4 GB vs 126 MB L2)"}
+                        f"global batch {b_gpu * world} = {b_gpu}/GPU x {world} ({args.scaling} scaling); heatmap: "
+                        f"{h_gpu * world} traces x {SEQ_LEN} points in total ({h_gpu}/GPU), 10 m x 10 m room, 0.05 m grid",
+            "global_batch": b_gpu * world, "batch_per_gpu": b_gpu, "seq_len": SEQ_LEN, "hidden": HIDDEN, "layers": LAYERS,
+            "precision": precision, "parallelism": f"dp{world}",
+            "l2": "inputs larger than L2 (train activations are GBs per step; heatmap input >= 0.5 GB per GPU vs 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -200,11 +221,114 @@ def timed(fn, steps, warmup, dist_on):
     return float(ms.item()) / steps
 
 
+class TrainLeg:
+    """One training configuration (model + flat buffers + optimizer + one synthetic batch resident on host and device)."""
+
+    def __init__(self, batch, rank, world, precision, dropout=0.0, seed_base=0):
+        from roomslam_b200 import RoomSLAM, synth
+        from roomslam_b200.train_utils import FlatParams, GradReducer, FusedAdamW, HostBatchPrefetcher
+        torch.manual_seed(0)
+        self.world, self.batch = world, batch
+        self.model = RoomSLAM(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=dropout,
+                              precision=precision).cuda().train()
+        self.flat = FlatParams(self.model)
+        self.reducer = GradReducer(self.flat)
+        self.opt = FusedAdamW(self.flat, lr=1e-3, max_grad_norm=1.0)
+        x_host, tgt_host = synth.make_sample(batch, SEQ_LEN, MAX_OBJECTS, seed=seed_base + rank)
+        self.x_host = x_host.pin_memory()
+        self.tgt_host = {k: v.pin_memory() for k, v in tgt_host.items()}
+        self.x_dev = self.x_host.cuda()
+        self.tgt_dev = {k: v.cuda() for k, v in self.tgt_host.items()}
+        self.loss_host = torch.zeros(6).pin_memory()
+        self.prefetch = HostBatchPrefetcher("cuda")
+        self.h2d_bytes = self.x_host.numel() * 4 + sum(v.numel() * v.element_size() for v in self.tgt_host.values())
+
+    def step(self, x, tgt):
+        self.flat.zero_grad()
+        self.reducer.prepare()
+        losses = self.model.compute_loss(self.model(x), tgt)
+        losses["total"].backward()
+        self.reducer.finish()
+        self.opt.step(grad_scale=1.0 / self.world)
+        return losses["total"]
+
+    def step_resident(self):
+        self.step(self.x_dev, self.tgt_dev)
+
+    def step_e2e(self):
+        # public-API training loop: every step copies ITS batch from pinned host memory (one copy per step, started while
+        # the previous step computes) and reads its loss back to the host
+        if not self.prefetch.has_pending:
+            self.prefetch.submit(self.x_host, self.tgt_host)
+        x, tgt = self.prefetch.get()
+        self.prefetch.submit(self.x_host, self.tgt_host)                            # next step's batch: overlaps this step
+        loss = self.step(x, tgt)
+        self.loss_host[0:1].copy_(loss.detach().reshape(1), non_blocking=True)      # device -> host read of the loss (pinned)
+
+    def free(self):
+        if self.prefetch.has_pending:
+            self.prefetch.get()
+        del self.x_dev, self.tgt_dev
+        torch.cuda.empty_cache()
+
+
+def invariance_check(world, rank):
+    """SURVEY.md 4(v) on the hardware: N shards + all-reduce against ONE GPU processing the concatenated batch.
+    Gradients: every trace has the same number of valid slots, so the global masked-mean loss is exactly the mean of the
+    shard losses and  sum_r grad_r / N  must equal the single-GPU gradient up to fp32 summation order.
+    Heatmap: the int32 sum of the shard grids must equal the grid of all points binned by one GPU, bit for bit."""
+    import torch.distributed as dist
+    from roomslam_b200 import RoomSLAM, OccupancyHeatmapBaseline, synth
+    from roomslam_b200.train_utils import FlatParams
+    out = {}
+    for precision, per_rank, tol in (("fp32", 64, 1e-5), ("bf16", TRAIN_BATCH // world, 1e-4)):
+        G = per_rank * world
+        x, tgt = synth.make_sample(G, SEQ_LEN, MAX_OBJECTS, seed=4242)
+        tgt["valid"] = torch.zeros_like(tgt["valid"])
+        tgt["valid"][:, :5] = 1
+        torch.manual_seed(0)
+        model = RoomSLAM(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=0.0, precision=precision).cuda().train()
+        flat = FlatParams(model)
+
+        def grads(lo, hi):
+            flat.zero_grad()
+            loss = model.compute_loss(model(x[lo:hi].cuda()), {k: v[lo:hi].cuda() for k, v in tgt.items()})["total"]
+            loss.backward()
+            return flat.grad.clone()
+        g = grads(rank * per_rank, (rank + 1) * per_rank)
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        g /= world
+        if rank == 0:
+            g1 = grads(0, G)
+            err = float((g.double() - g1.double()).norm() / g1.double().norm().clamp_min(1e-30))
+            out[f"grad_rel_l2_{precision}"] = err
+            out[f"grad_ok_{precision}"] = bool(err <= tol)
+            out[f"grad_tol_{precision}"] = tol
+            out[f"grad_global_batch_{precision}"] = G
+        del model, flat, g
+        torch.cuda.empty_cache()
+    # heatmap: HEATMAP_TRACES in total, shard r = traces [r n, (r+1) n)
+    hm = OccupancyHeatmapBaseline()
+    n = HEATMAP_TRACES // world
+    pts = synth.make_traces(n, SEQ_LEN, seed=7000 + rank, device="cuda")
+    occ, stat, dropped = hm.bin(pts)
+    both = torch.cat([occ.reshape(-1), stat.reshape(-1), torch.tensor([dropped], device="cuda", dtype=torch.int64).to(torch.int32)])
+    dist.all_reduce(both, op=dist.ReduceOp.SUM)
+    allpts = torch.empty(world * n, SEQ_LEN, 2, device="cuda") if rank == 0 else None
+    dist.gather(pts, list(allpts.view(world, n, SEQ_LEN, 2).unbind(0)) if rank == 0 else None, dst=0)
+    if rank == 0:
+        o1, s1, d1 = hm.bin(allpts)
+        one = torch.cat([o1.reshape(-1), s1.reshape(-1), torch.tensor([d1], device="cuda", dtype=torch.int32)])
+        out["heatmap_bit_identical"] = bool(torch.equal(one, both))
+        out["heatmap_traces"] = world * n
+        out["invariance"] = bool(out["heatmap_bit_identical"] and out["grad_ok_fp32"] and out["grad_ok_bf16"])
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from roomslam_b200 import RoomSLAM, OccupancyHeatmapBaseline, synth, _lib
+    from roomslam_b200 import OccupancyHeatmapBaseline, synth, _lib
     from roomslam_b200 import functional as F_
-    from roomslam_b200.train_utils import FlatParams, GradReducer, FusedAdamW, HostBatchPrefetcher
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,78 +344,62 @@ def run_ours(args):
     args.gpus = world
     pk = peaks()
     lib = _lib.load()
-    precision = args.precision
-    if precision == "auto":
-        try:
-            import roomslam_b200.functional_bf16  # noqa: F401
-            precision = "bf16"
-        except ImportError:
-            precision = "fp32"
+    precision = "bf16" if args.precision == "auto" else args.precision
+    B, n_tr = shard_sizes(args, world)                     # per GPU, headline leg
+    other = "weak" if args.scaling == "strong" else "strong"
 
-    # ---- training step -------------------------------------------------------------------------------------
-    torch.manual_seed(0)
-    model = RoomSLAM(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=0.0, precision=precision).cuda()
-    model.train()
-    flat = FlatParams(model)
-    reducer = GradReducer(flat)
-    opt = FusedAdamW(flat, lr=1e-3, max_grad_norm=1.0)
-    B = args.batch
-    x_host, tgt_host = synth.make_sample(B, SEQ_LEN, MAX_OBJECTS, seed=rank)
-    x_host = x_host.pin_memory()
-    tgt_host = {k: v.pin_memory() for k, v in tgt_host.items()}
-    x_dev = x_host.cuda()
-    tgt_dev = {k: v.cuda() for k, v in tgt_host.items()}
-    loss_host = torch.zeros(6).pin_memory()
-
-    def step(x, tgt):
-        flat.zero_grad()
-        reducer.prepare()
-        losses = model.compute_loss(model(x), tgt)
-        losses["total"].backward()
-        reducer.finish()
-        opt.step(grad_scale=1.0 / world)
-        return losses["total"]
-
-    def step_resident():
-        step(x_dev, tgt_dev)
-
-    prefetch = HostBatchPrefetcher("cuda")
-
-    def step_e2e():
-        # public-API training loop: every step copies ITS batch from pinned host memory (one copy per step, started while
-        # the previous step computes) and reads its loss back to the host
-        if not prefetch.has_pending:
-            prefetch.submit(x_host, tgt_host)
-        x, tgt = prefetch.get()
-        prefetch.submit(x_host, tgt_host)                                      # next step's batch: overlaps this step
-        loss = step(x, tgt)
-        loss_host[0:1].copy_(loss.detach().reshape(1), non_blocking=True)      # device -> host read of the loss (pinned)
-
+    # ---- training step: headline leg -----------------------------------------------------------------------
+    leg = TrainLeg(B, rank, world, precision)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = lib.rs_launch_count()
-    ms_train = timed(step_resident, args.steps, args.warmup, dist_on)
+    ms_train = timed(leg.step_resident, args.steps, args.warmup, dist_on)
     launches_train = (lib.rs_launch_count() - n0) // (args.steps + args.warmup) * args.steps
-    ms_train_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), dist_on)
-    h2d_train = x_host.numel() * 4 + sum(v.numel() * v.element_size() for v in tgt_host.values())
-    final_loss = float(loss_host[0])
-
+    ms_train_e2e = timed(leg.step_e2e, args.steps, max(1, args.warmup // 2), dist_on)
+    h2d_train = leg.h2d_bytes
+    final_loss = float(leg.loss_host[0])
     # per-kernel timing of one extra step (CUDA events on the launch stream) for the roofline object
-    prof = F_.enable_kernel_timing(True) if hasattr(F_, "enable_kernel_timing") else None
-    if prof is not None:
-        step_resident()
-        torch.cuda.synchronize()
-        kernel_ms = F_.collect_kernel_timing()
-        F_.enable_kernel_timing(False)
-    else:
-        kernel_ms = {}
-    del x_dev, tgt_dev
-    torch.cuda.empty_cache()
+    F_.enable_kernel_timing(True)
+    leg.step_resident()
+    torch.cuda.synchronize()
+    kernel_ms = F_.collect_kernel_timing()
+    F_.enable_kernel_timing(False)
+    leg.free()
+    del leg
+
+    # ---- the other scaling mode (N > 1 only; at N = 1 the two coincide) ---------------------------------------
+    other_leg = None
+    if dist_on:
+        args_o = argparse.Namespace(**{**vars(args), "scaling": other})
+        B_o, n_tr_o = shard_sizes(args_o, world)
+        leg_o = TrainLeg(B_o, rank, world, precision)
+        ms_o = timed(leg_o.step_resident, args.steps, args.warmup, dist_on)
+        ms_o_e2e = timed(leg_o.step_e2e, max(2, args.steps // 2), 2, dist_on)
+        leg_o.free()
+        del leg_o
+        other_leg = {"scaling": other, "global_batch": B_o * world, "batch_per_gpu": B_o, "value": B_o * world / (ms_o / 1e3),
+                     "unit": "traces/s", "ms_per_step": ms_o, "e2e_value": B_o * world / (ms_o_e2e / 1e3)}
+
+    # ---- single-GPU extras: BASELINE config 1 on the GPU (same config as the CPU arm), dropout = 0.1 ---------------
+    c1 = drop = None
+    if not dist_on:
+        c1_leg = TrainLeg(32, 0, 1, "fp32")
+        ms_c1 = timed(c1_leg.step_resident, max(args.steps, 10), 3, False)
+        c1_leg.free()
+        del c1_leg
+        c1 = {"workload": "BASELINE config 1: batch 32 x 500 steps, fp32 kernels (1e-4 parity mode), fwd+loss+bwd+clip+AdamW",
+              "value": 32 / (ms_c1 / 1e3), "unit": "traces/s", "ms_per_step": ms_c1, "precision": "fp32", "batch": 32}
+        d_leg = TrainLeg(B, 0, 1, precision, dropout=0.1)
+        ms_d = timed(d_leg.step_resident, args.steps, 3, False)
+        d_leg.free()
+        del d_leg
+        drop = {"workload": "same step with the README's inter-layer dropout p = 0.1 (bit mask drawn on the device, applied inside "
+                            "the recurrence kernels)", "value": B / (ms_d / 1e3), "unit": "traces/s", "ms_per_step": ms_d,
+                "slowdown_vs_p0": ms_d / ms_train - 1.0}
 
     # ---- heatmap -------------------------------------------------------------------------------------------
     hm = OccupancyHeatmapBaseline()
-    n_tr = args.heatmap_traces
     pts = synth.make_traces(n_tr, SEQ_LEN, seed=1000 + rank, device="cuda")
     occ = torch.empty(hm.gy, hm.gx, dtype=torch.int32, device="cuda")
     stat = torch.empty_like(occ)
@@ -324,16 +432,29 @@ def run_ours(args):
             both.cpu()
 
     ms_heat_e2e = timed(heat_e2e, max(1, min(args.steps, 3)), 1, dist_on)
+    del pts_host
+    heat_other = None
+    if dist_on:
+        pts_o = synth.make_traces(n_tr_o, SEQ_LEN, seed=2000 + rank, device="cuda")
+        ms_ho = timed(lambda: (hm.bin_into(pts_o, occ, stat, dropped), packed[: hm.gx * hm.gy].copy_(occ.reshape(-1)),
+                               packed[hm.gx * hm.gy:].copy_(stat.reshape(-1)), dist.all_reduce(packed, op=dist.ReduceOp.SUM)),
+                      args.steps, args.warmup, True)
+        heat_other = {"scaling": other, "traces_per_gpu": n_tr_o, "value": n_tr_o * SEQ_LEN * world / (ms_ho / 1e3) / 1e9,
+                      "unit": "Gpoints/s", "ms_per_step": ms_ho}
+        del pts_o
+        torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
+    inv = invariance_check(world, rank) if dist_on else None
 
     if rank == 0:
         traces_s = B * world / (ms_train / 1e3)
         flops = gru_flops_per_trace()
+        traffic = load_traffic()
         line = {
             "metric": METRIC, "value": traces_s, "unit": "traces/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_train, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_train, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args, precision),
+            "config": workload_config(args, precision, world),
             "e2e": {"value": B * world / (ms_train_e2e / 1e3), "unit": "traces/s", "h2d_bytes_per_step": h2d_train,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_train_e2e},
             "gpu_launches": int(launches_train + launches_heat),
@@ -350,17 +471,28 @@ def run_ours(args):
                         "ms_per_step": ms_heat_e2e},
                 "roofline": {"bound": "hbm", "achieved": n_tr * SEQ_LEN * 8 / (ms_kernel / 1e3) / 1e9, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": n_tr * SEQ_LEN * 8 / (ms_kernel / 1e3) / 1e9 / pk["hbm_gbs"],
-                             # dram__bytes_read+write of one `ncu --set full` capture (profiles/r1_heatmap_ncu.md):
-                             # 1.648 GB for 2e8 points = 8.24 B/point, scaled to this launch's point count
-                             "traffic": int(8.24 * n_tr * SEQ_LEN), "kernel": "heatmap_tma_kernel", "kernel_ms": ms_kernel,
+                             "traffic": (int(traffic["heatmap_bytes_per_point"] * n_tr * SEQ_LEN)
+                                         if traffic and "heatmap_bytes_per_point" in traffic else None),
+                             "traffic_source": traffic.get("source") if traffic else None,
+                             "kernel": "heatmap_tma_kernel", "kernel_ms": ms_kernel,
                              "algorithmic_bytes_per_point": 8, "algorithmic_bytes": 8 * n_tr * SEQ_LEN,
                              "peak_source": pk["source"] + ", burst (kernel timed alone)"},
             },
         }
-        line["roofline"] = train_roofline(kernel_ms, B, pk, precision) or line["heatmap"]["roofline"]
+        line["roofline"] = train_roofline(kernel_ms, B, pk, precision, traffic) or line["heatmap"]["roofline"]
+        if other_leg is not None:
+            line[other] = other_leg
+            line["heatmap"][other] = heat_other
+        if inv is not None:
+            line["invariance"] = inv.pop("invariance")
+            line["invariance_detail"] = inv
+        if c1 is not None:
+            line["c1"] = c1
+            line["dropout"] = drop
         if world == 1:
             cb = cpu_train_baseline(2, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["c1"]["cpu_same_config"] = {"value": cb["value"], "unit": "traces/s", "ratio": line["c1"]["value"] / cb["value"]}
             line["heatmap"]["cpu_baseline"] = cpu_heatmap_baseline()
         print(json.dumps(line), flush=True)
     if dist_on:
@@ -533,12 +665,17 @@ def run_next_rows(args):
 
 
 
-# DRAM bytes per launch of the training step's kernels at the benchmark shape (8192 traces x 500 steps per GPU, bf16), from
-# `ncu --set full` captures of tools/step_once.py 8192 (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_step_kernels_ncu.md)
-NCU_TRAFFIC_B8192 = {"rec_bwd_bf16_kernel": 20.947e9, "blk_wgrad_kernel": (16.472e9 + 12.712e9) / 2}
+def load_traffic():
+    """DRAM bytes per launch from the round's committed `ncu --set full` captures (profiles/r2_traffic.json, stamped
+    with the commit they were taken at): {"commit", "source", "batch_per_gpu", "kernels": {name: bytes}, "heatmap_bytes_per_point"}."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
 
 
-def train_roofline(kernel_ms, B, pk, precision):
+def train_roofline(kernel_ms, B, pk, precision, traffic):
     """Roofline object for the kernel with the largest share of the training step."""
     if not kernel_ms:
         return None
@@ -550,15 +687,14 @@ def train_roofline(kernel_ms, B, pk, precision):
            "frac": ach / pk["tflops_sustained"], "traffic": None, "kernel": name, "kernel_ms": ms, "launches": calls,
            "algorithmic_flops": flops,
            "note": "dominant kernel of the training step by CUDA-event time; the tensor figure is the algorithmic-FLOP view "
-                   "SURVEY.md 8(d) asks for. In practice the kernel is bound by the HBM traffic of saved activations "
-                   "(DESIGN.md 4.2): see hbm_view",
+                   "SURVEY.md 8(d) asks for. Its achieved HBM bandwidth over the measured DRAM bytes is in hbm_view",
            "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)"}
-    if precision == "bf16" and B == TRAIN_BATCH and name in NCU_TRAFFIC_B8192:
-        per_launch = NCU_TRAFFIC_B8192[name]
+    per_launch = (traffic or {}).get("kernels", {}).get(name)
+    if precision == "bf16" and traffic and B == traffic.get("batch_per_gpu") and per_launch:
         gbs = per_launch / (ms / calls / 1e3) / 1e9
         out["traffic"] = per_launch
         out["hbm_view"] = {"bytes_per_launch": per_launch, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                           "frac": gbs / pk["hbm_gbs"], "source": "ncu --set full, one capture per launch (profiles/r1_step_kernels_ncu.md)"}
+                           "frac": gbs / pk["hbm_gbs"], "source": traffic.get("source"), "commit": traffic.get("commit")}
     return out
 
 
@@ -569,8 +705,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="traces per GPU")
-    ap.add_argument("--heatmap-traces", type=int, default=HEATMAP_TRACES, help="traces per GPU")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE config 3): --batch / --heatmap-traces are GLOBAL and split over the GPUs; "
+                         "weak: they are per GPU.  The other mode is measured too and reported under its name")
+    ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="traces (global for strong scaling, per GPU for weak)")
+    ap.add_argument("--heatmap-traces", type=int, default=HEATMAP_TRACES, help="traces (global / per GPU, as --batch)")
     ap.add_argument("--suite", default="headline", choices=["headline", "next"],
                     help="'next': one JSON line per SURVEY.md 8(f) row instead of the headline line (single GPU)")
     args = ap.parse_args()

@@ -161,13 +161,22 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
  * weights / biases carry the factor 1/2 of sigma(a) = tanh(a/2)/2 + 1/2.  b_hn [2][H], out tile-major (2H columns,
  * zero pad rows), gates [tiles][T][2][64][128][8] fp16 (NULL for inference), h_n [2][B][H] fp32. */
 int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
-                    void* gates, float* h_n, const int* lengths, int B, int T, void* stream);
+                    void* gates, float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale,
+                    void* out_drop, int B, int T, void* stream);
 /* x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (zero padded): layer-0 input for rs_blk_wgrad. */
 int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 /* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
  * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                    const int* lengths, int B, int T, void* stream);
+                    const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T, void* stream);
+/* Inter-layer dropout (README.md:114; analogue src/benchmark/model.py:13,20) without a (B, T, 2H) multiply in HBM: the
+ * mask travels as ONE BIT per element, [tiles][T][128 rows][C/8 bytes] (C = 2H), plus a device scalar scale = 1/keep.
+ * rs_rec_fwd_bf16 with drop_bits writes out_drop = out (.) mask * scale next to out (the next layer's input);
+ * rs_rec_bwd_bf16 with drop_bits multiplies the incoming d_out by the same mask.  rs_pack_drop_mask packs an explicit
+ * (B, T, C) fp32 mask (decision D4: values 0 or 1/keep; scale = its maximum); rs_gen_drop_bits draws Bernoulli(keep)
+ * bits from a counter-based hash of (seed, position) directly on the device. */
+int rs_pack_drop_mask(const float* mask, int B, int T, int C, void* bits, float* scale, void* stream);
+int rs_gen_drop_bits(void* bits, int B, int T, int C, float keep, uint64_t seed, float* scale, void* stream);
 
 /* ---- on-GPU trace preprocessing (replaces src/benchmark/dataloader.py:410-457 _process_traces
  *      = src/benchmark/inference.py:24-57 process_traces, plus the padding of collate_fn dataloader.py:510-559) ------ */

@@ -17,9 +17,12 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "rec_common.cuh"
 #include "../../include/roomslam_b200.h"
 
 namespace {
+
+using namespace rs;
 
 constexpr int H = 128;
 constexpr int CHUNK = 2048;                 // bytes of one 16-byte chunk column over 128 rows
@@ -43,63 +46,6 @@ struct FwdParams {
     int B, T;
     int pf_dist;                            // L2 prefetch distance in steps (0 = off)
 };
-
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
-    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
-    return __bfloat1622float2(h);
-}
-__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
-    float2 a = bf2_to_f2(v.x), b = bf2_to_f2(v.y), c = bf2_to_f2(v.z), d = bf2_to_f2(v.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-    return make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]), f2_to_bf2(f[6], f[7]));
-}
-// saved gates are private to the two recurrence kernels: fp16 (r, z, n live in [-1, 1], where fp16 is 8x finer than bf16)
-__device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint4 pack8h(const float* f) {
-    return make_uint4(f2_to_h2(f[0], f[1]), f2_to_h2(f[2], f[3]), f2_to_h2(f[4], f[5]), f2_to_h2(f[6], f[7]));
-}
-__device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-        f[2 * i] = t.x; f[2 * i + 1] = t.y;
-    }
-}
-__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ void stg16(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
-
-// Layer-0 input columns of one trace row: per input c the triple (hi, lo, hi) with hi = bf16(x_c), lo = bf16(x_c - hi),
-// then (1, 1); at most 2 inputs fit the 8 columns of one 16-byte chunk.
-__device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
-    float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (xp) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            if (i < I) {
-                const float v = __ldg(xp + i);
-                const float hi = __bfloat162float(__float2bfloat16_rn(v));
-                c[3 * i] = hi; c[3 * i + 1] = v - hi; c[3 * i + 2] = hi;
-            }
-        }
-    }
-    c[6] = 1.0f; c[7] = 1.0f;
-    return pack8(c);
-}
 
 template <bool kVarLen>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdParams p) {
@@ -534,8 +480,8 @@ int pf_dist_env(const char* name, int dflt) {
 }  // namespace
 
 extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh,
-                               const float* b_hn, void* out, void* gates, float* h_n, const int* lengths, int B, int T,
-                               void* stream_) {
+                               const float* b_hn, void* out, void* gates, float* h_n, const int* lengths,
+                               const void* drop_bits, const float* drop_scale, void* out_drop, int B, int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -547,6 +493,11 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
         RS_CUDA_OK(cudaMemsetAsync(h_n, 0, sizeof(float) * 2 * (size_t)B * H, stream));
         return 0;
     }
+    RS_REQUIRE((drop_bits != nullptr) == (out_drop != nullptr) && (!drop_bits || drop_scale),
+               "rs_rec_fwd_bf16: drop_bits, drop_scale and out_drop go together");
+    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr))
+        return rs::rec_fwd_pair(x, I, P, Whh, b_hn, out, gates, h_n, lengths, drop_bits, drop_scale, out_drop, B, T, nt,
+                                pf_dist_env("RS_PF_DIST_FWD", 1), stream);
     FwdParams p = {};
     p.x = x; p.I = I;
     p.P = static_cast<const uint8_t*>(P); p.p_block_bytes = 6LL * H * 256;
@@ -568,11 +519,15 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
 }
 
 extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT,
-                               void* dG, const int* lengths, int B, int T, void* stream_) {
+                               void* dG, const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T,
+                               void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(gates && out && WhhT && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
+    RS_REQUIRE(!drop_bits || drop_scale, "rs_rec_bwd_bf16: drop_bits needs drop_scale");
+    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr))
+        return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, dG, lengths, drop_bits, drop_scale, B, T, nt, stream);
     BwdParams p = {};
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);

@@ -1,0 +1,634 @@
+// Persistent tensor-core GRU recurrence on a CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2), H = 128:
+// forward and backward through time.  Same operands, layouts and results as rec_bf16.cu
+// (one CTA per 128-trace tile); what changes is how a tile is spread over the chip:
+//
+//   * A pair of CTAs on one TPC owns a 128-trace tile of one direction; each CTA holds 64 of its traces.  One thread of
+//     the even CTA issues M = 128 MMAs that span both SMs.  In that mode the accumulator of a CTA uses ALL 128 TMEM lanes
+//     for its 64 rows: lane = row + 64 * (column half), so the epilogue of a tile runs on 2 x 128 lanes instead of 128 --
+//     half the serial epilogue chain per step -- and each CTA needs only HALF of W_hh in shared memory (the tensor core
+//     fetches the other half from the peer): the gate rows of hidden units [64 rank, 64 rank + 64).
+//   * No activation crosses the pair in software: the two lane halves of a CTA produce all 128 hidden units of its 64
+//     rows, written straight into its own A-operand tile.  Only mbarrier arrivals (epilogue warps -> the issuing CTA)
+//     and the multicast tcgen05.commit cross the pair.
+//   * With half the footprint per tile a pair carries NT = 2 tiles in flight (2 x 256 TMEM columns, 16 epilogue warps):
+//     the MMA of one tile runs under the epilogue of the other, and every scheduler has 4 epilogue warps to pick from.
+//     Small batches run NT = 1 on twice as many SMs (the latency-bound regime of strong scaling, BASELINE config 3).
+//   * Inter-layer dropout (README.md:114) is applied here from a bit-packed mask: the forward kernel of a layer also writes
+//     out (.) mask as the next layer's input, the backward kernel masks the incoming d_out.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "rec_common.cuh"
+#include "../../include/roomslam_b200.h"
+
+namespace {
+
+using namespace rs;
+
+constexpr int H = 128;
+constexpr int ROWS = 64;                        // traces of a tile held by one CTA of the pair
+constexpr int CHUNK_G = 2048;                   // global: one 16-byte chunk column over the 128 rows of a tile
+constexpr int CHUNK_S = ROWS * 16;              // shared: the same over this CTA's 64 rows
+constexpr int W_CHUNK = 192 * 16;               // shared: one chunk column of this CTA's W_hh rows (r | z | hn of 64 units)
+constexpr int W_FWD_BYTES = 18 * W_CHUNK;       // 54 KB (16 hidden chunks + 2 layer-0 input chunks)
+constexpr int A_FWD_BYTES = 18 * CHUNK_S;       // 18 KB per tile in flight
+constexpr int H32_BYTES = (H / 4) * CHUNK_S;    // 32 KB per tile in flight (fp32 master copy of h)
+constexpr int W_BWD_BYTES = 48 * CHUNK_S;       // 48 KB: W_hh^T rows of this CTA's 64 hidden units, K = 384 gate rows
+constexpr int A_BWD_BYTES = 48 * CHUNK_S;       // 48 KB per tile in flight (dGh)
+constexpr int EPI_WARPS = 8;                    // per tile in flight: 4 TMEM lane quadrants x 2 groups of 32 hidden units
+
+struct FwdPairParams {
+    const float* x; int I;
+    const uint8_t* P; long long p_block_bytes;
+    const uint8_t* Whh;                     // [2][16 or 18][384][8] bf16 (the image rs_rec_fwd_bf16 documents)
+    const float* b_hn;
+    uint8_t* out; long long out_block_bytes;
+    uint8_t* gates;
+    float* h_n;
+    const int* lengths;
+    const uint8_t* drop_bits;               // [tiles][T][128 rows][32] one bit per (trace, step, output column) or NULL
+    const float* drop_scale;                // device scalar 1 / keep
+    uint8_t* out_drop;                      // tile-major like out: out (.) mask, the next layer's input (with drop_bits)
+    int B, T, n_tiles;
+    int pf_dist;
+};
+
+template <int NT, bool kVarLen, bool kFusedX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) rec_fwd_pair_kernel(const FwdPairParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;                                   // [18 chunks][192 rows][16 B]
+    uint8_t* a_s = w_s + W_FWD_BYTES;                      // [NT][18 chunks][64 rows][16 B]  h_{t-1} | input columns
+    uint8_t* h32_s = a_s + NT * A_FWD_BYTES;               // [NT][32 chunks of 4 floats][64 rows][16 B]
+    float* bhn_s = reinterpret_cast<float*>(h32_s + NT * H32_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bhn_s + H);
+    uint64_t* w_full = bars;
+    uint64_t* h_ready = bars + 1;               // [NT], the even CTA's copies collect the arrivals of BOTH CTAs
+    uint64_t* acc_full = bars + 1 + NT;         // [NT], one per CTA (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NT);
+
+    const uint32_t rank = cluster_ctarank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+    const int tile0 = (blockIdx.x >> 1) * NT;
+    const int n_slots = min(NT, p.n_tiles - tile0);
+    const int T = p.T;
+    constexpr bool fused_x = kFusedX;
+    constexpr int n_chunks = fused_x ? 18 : 16;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < NT; ++s) {
+            mbar_init(&h_ready[s], 2 * EPI_WARPS);
+            mbar_init(&acc_full[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc_pair<256 * NT>(tmem_slot);
+        if (lane == 0) {            // this CTA's half of W_hh: per chunk the r, z, n rows of its 64 hidden units
+            mbar_expect_tx(w_full, n_chunks * W_CHUNK);
+            const uint8_t* src = p.Whh + (long long)dir * n_chunks * (384 * 16);
+            for (int c = 0; c < n_chunks; ++c)
+                for (int g = 0; g < 3; ++g)
+                    bulk_load(w_s + c * W_CHUNK + g * 1024, src + (long long)c * (384 * 16) + (g * 128 + rank * 64) * 16, 1024, w_full);
+        }
+    }
+    for (int i = threadIdx.x; i < H; i += blockDim.x) bhn_s[i] = p.b_hn[dir * H + i];
+    for (int i = threadIdx.x; i < NT * (A_FWD_BYTES + H32_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (fused_x && threadIdx.x < ROWS * NT) {           // input columns of the first step
+        const int s = threadIdx.x / ROWS, rl = threadIdx.x % ROWS;
+        const long long b = (long long)(tile0 + s) * 128 + rank * ROWS + rl;
+        *reinterpret_cast<uint4*>(a_s + s * A_FWD_BYTES + 16 * CHUNK_S + rl * 16) =
+            pack_x((s < n_slots && b < p.B) ? p.x + (b * T + (dir ? T - 1 : 0)) * p.I : nullptr, p.I);
+    }
+    fence_proxy_async();
+    if (warp == 0) mbar_wait(w_full, 0);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();             // both CTAs: barriers initialised, TMEM allocated, W and the first A tiles in place
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (rank == 0) {
+            // ===================== MMA issuer for the pair =====================
+            constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0);
+            constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
+            const uint32_t w_addr = smem_u32(w_s);
+            for (int step = 0; step < T; ++step) {
+                for (int s = 0; s < n_slots; ++s) {
+                    if (step > 0) {
+                        mbar_wait_cluster(&h_ready[s], (step - 1) & 1);
+                        tc_fence_after();
+                    }
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(a_s + s * A_FWD_BYTES);
+                        const uint32_t d = tmem_base + s * 256;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            const uint64_t db0 = umma_desc_noswz(w_addr + k * 2 * W_CHUNK, W_CHUNK, 128);
+                            const uint64_t db1 = umma_desc_noswz(w_addr + k * 2 * W_CHUNK + 128 * 16, W_CHUNK, 128);
+                            tc_mma_bf16_pair(d, da, db0, idesc256, k != 0);           // r | z  -> columns [0, 128) of each lane half
+                            tc_mma_bf16_pair(d + 128, da, db1, idesc128, k != 0);     // W_hn h -> columns [128, 192)
+                        }
+                        if (fused_x) {      // layer 0: W_ih x + b as one more K = 16 step of hi / lo split operands
+                            const uint64_t da = umma_desc_noswz(a_addr + 16 * CHUNK_S, CHUNK_S, 128);
+                            const uint64_t db0 = umma_desc_noswz(w_addr + 16 * W_CHUNK, W_CHUNK, 128);
+                            const uint64_t db1 = umma_desc_noswz(w_addr + 16 * W_CHUNK + 128 * 16, W_CHUNK, 128);
+                            tc_mma_bf16_pair(d, da, db0, idesc256, 1u);
+                            tc_mma_bf16_pair(d + 192, da, db1, idesc128, 0u);         // W_in x + b_in -> columns [192, 256)
+                        }
+                        tc_commit_pair(&acc_full[s]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== L2 prefetcher: this CTA pulls half of the next projection block =====================
+        if (lane == 0 && !kFusedX && p.pf_dist > 0) {
+            for (int step = 0; step < T; ++step) {
+                const int t = dir ? (T - 1 - step) : step;
+                for (int s = 0; s < n_slots; ++s) {
+                    const long long blk = (long long)(tile0 + s) * (T + 2) + t + 1;
+                    l2_prefetch(p.P + blk * p.p_block_bytes + (long long)(dir * 48 + rank * 24) * CHUNK_G, 24 * CHUNK_G);
+                }
+                if (step >= p.pf_dist) mbar_wait(&acc_full[0], (step - p.pf_dist) & 1);
+            }
+        }
+    } else if ((warp - 2) / EPI_WARPS < n_slots) {
+        // ===================== epilogue: gates, blend, stores =====================
+        const int s = (warp - 2) / EPI_WARPS;
+        const int wg = ((warp - 2) % EPI_WARPS) >> 2;      // which 32 of this lane half's 64 hidden units
+        const int q = warp & 3;                            // TMEM lane quadrant of this warp
+        const int uh = q >> 1;                             // lane half = hidden-unit half
+        const int rl = (q & 1) * 32 + lane;                // row within this CTA
+        const int row = rank * ROWS + rl;                  // row within the 128-trace tile
+        const int tile = tile0 + s;
+        const long long b = (long long)tile * 128 + row;
+        const bool live = b < p.B;
+        const int ub = uh * 64 + wg * 32;                  // first hidden unit of this thread
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 256 + wg * 32;
+        uint8_t* a_row = a_s + s * A_FWD_BYTES + rl * 16;
+        uint8_t* h32_row = h32_s + s * H32_BYTES + rl * 16;
+        const uint32_t hr_remote = mapa_cluster(smem_u32(&h_ready[s]), 0);
+        const float* xrow = p.x ? p.x + b * T * p.I : nullptr;
+        const int len = (kVarLen && live) ? p.lengths[b] : T;
+        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? (T - 1 - step) : step;
+            const bool active = !kVarLen || t < len;
+            const long long blk = (long long)tile * (T + 2) + t + 1;
+            const uint8_t* pblk = kFusedX ? nullptr : p.P + blk * p.p_block_bytes + (long long)(dir * 48 + ub / 8) * CHUNK_G + row * 16;
+            const long long o_off = blk * p.out_block_bytes + (long long)(dir * 16 + ub / 8) * CHUNK_G + row * 16;
+            uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
+            uint32_t dbits = 0;
+            if (p.drop_bits) dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + ub / 8));
+            uint4 xnext = make_uint4(0, 0, 0, 0);
+            const bool write_x = fused_x && ub == 0 && step + 1 < T;
+            if (write_x) xnext = pack_x(live ? xrow + (long long)(dir ? t - 1 : t + 1) * p.I : nullptr, p.I);
+            uint4 pv[3];
+            auto load_p = [&](int grp) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g) pv[g] = ldg16(pblk + (long long)(g * 16 + grp) * CHUNK_G);
+            };
+            if (!kFusedX) load_p(0);
+            mbar_wait(&acc_full[s], step & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int grp = 0; grp < 4; ++grp) {
+                const int u0 = ub + grp * 8;
+                uint32_t ar[8], az[8], an[8], ax[8];
+                tmem_ld_32x32b_x8(taddr + grp * 8, ar);
+                tmem_ld_32x32b_x8(taddr + 64 + grp * 8, az);
+                tmem_ld_32x32b_x8(taddr + 128 + grp * 8, an);
+                if (kFusedX) tmem_ld_32x32b_x8(taddr + 192 + grp * 8, ax);
+                uint4 pc[3];
+                if (!kFusedX) {
+                    pc[0] = pv[0]; pc[1] = pv[1]; pc[2] = pv[2];
+                    if (grp < 3) load_p(grp + 1);
+                }
+                tmem_ld_wait();
+                uint32_t wo[4], wd[4], wr[4], wz[4], wn[4], wh[4];      // packed outputs: h, h (.) mask, r, z, n, hn
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {                        // two hidden units at a time keeps the live set small
+                    float hv2[2], rv2[2], zv2[2], nv2[2], hnv2[2], od2[2];
+                    const float2 ho2 = *reinterpret_cast<const float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8);
+                    const float2 bh2 = *reinterpret_cast<const float2*>(bhn_s + u0 + 2 * jp);
+                    float2 pr2 = make_float2(0.f, 0.f), pz2 = pr2, pn2 = pr2;
+                    if (!kFusedX) {
+                        const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&pc[0]);
+                        const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&pc[1]);
+                        const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&pc[2]);
+                        pr2 = bf2_to_f2(w0[jp]); pz2 = bf2_to_f2(w1[jp]); pn2 = bf2_to_f2(w2[jp]);
+                    } else {            // layer 0: the tensor core already added W_ih x + b to r and z
+                        pn2 = make_float2(__uint_as_float(ax[2 * jp]), __uint_as_float(ax[2 * jp + 1]));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 2 * jp + e;
+                        const float ho = e ? ho2.y : ho2.x;
+                        // the 1/2 of sigma(a) = 1/2 tanh(a/2) + 1/2 is folded into the r and z rows of the weights and biases
+                        const float r = fmaf(0.5f, tanh_fast(__uint_as_float(ar[j]) + (e ? pr2.y : pr2.x)), 0.5f);
+                        const float z = active ? fmaf(0.5f, tanh_fast(__uint_as_float(az[j]) + (e ? pz2.y : pz2.x)), 0.5f) : 1.0f;
+                        const float hn = __uint_as_float(an[j]) + (e ? bh2.y : bh2.x);
+                        const float n = tanh_fast(fmaf(r, hn, e ? pn2.y : pn2.x));
+                        const float h = active ? fmaf(z, ho - n, n) : ho;
+                        hv2[e] = h; rv2[e] = r; zv2[e] = z; nv2[e] = n; hnv2[e] = hn;
+                        od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
+                    }
+                    *reinterpret_cast<float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8) = make_float2(hv2[0], hv2[1]);
+                    wo[jp] = f2_to_bf2(hv2[0], hv2[1]);
+                    wd[jp] = f2_to_bf2(od2[0], od2[1]);
+                    wr[jp] = f2_to_h2(rv2[0], rv2[1]); wz[jp] = f2_to_h2(zv2[0], zv2[1]);
+                    wn[jp] = f2_to_h2(nv2[0], nv2[1]); wh[jp] = f2_to_h2(hnv2[0], hnv2[1]);
+                    if (step == T - 1 && live)
+                        *reinterpret_cast<float2*>(p.h_n + ((long long)dir * p.B + b) * H + u0 + 2 * jp) = make_float2(hv2[0], hv2[1]);
+                }
+                const uint4 o0 = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+                *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK_S) = o0;      // next step's A operand, in place
+                stg16(p.out + o_off + (long long)grp * CHUNK_G, active ? o0 : make_uint4(0, 0, 0, 0));
+                if (p.out_drop) stg16(p.out_drop + o_off + (long long)grp * CHUNK_G, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+                if (gblk) {
+                    stg16(gblk + (long long)(0 * 16 + grp) * CHUNK_G, make_uint4(wr[0], wr[1], wr[2], wr[3]));
+                    stg16(gblk + (long long)(1 * 16 + grp) * CHUNK_G, make_uint4(wz[0], wz[1], wz[2], wz[3]));
+                    stg16(gblk + (long long)(2 * 16 + grp) * CHUNK_G, make_uint4(wn[0], wn[1], wn[2], wn[3]));
+                    stg16(gblk + (long long)(3 * 16 + grp) * CHUNK_G, make_uint4(wh[0], wh[1], wh[2], wh[3]));
+                }
+            }
+            if (write_x) *reinterpret_cast<uint4*>(a_row + 16 * CHUNK_S) = xnext;
+            fence_proxy_async();        // h_t written with ordinary stores -> visible to the tensor core of this SM
+            tc_fence_before();          // TMEM reads done before the next MMA overwrites the accumulator
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(hr_remote);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's tensor core reads this CTA's W half until its last MMA retired
+    if (warp == 0) tmem_dealloc_pair<256 * NT>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct BwdPairParams {
+    const uint8_t* d_out; long long dout_block_bytes;
+    const float* d_h_n;
+    const uint8_t* gates;
+    const uint8_t* out; long long out_block_bytes;
+    const uint8_t* WhhT;                                 // [2][48][128][8] bf16
+    uint8_t* dG; long long dg_block_bytes;
+    const int* lengths;
+    const uint8_t* drop_bits;                            // mask of THIS layer's output (applied to d_out) or NULL
+    const float* drop_scale;
+    int B, T, n_tiles;
+};
+
+template <int NT, bool kVarLen>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) rec_bwd_pair_kernel(const BwdPairParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_s = smem;                                   // [48 chunks][64 rows = hidden units of this CTA][16 B]
+    uint8_t* a_s = w_s + W_BWD_BYTES;                      // [NT][48 chunks][64 rows][16 B]  dGh_t
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + NT * A_BWD_BYTES);
+    uint64_t* w_full = bars;
+    uint64_t* a_ready = bars + 1;               // [NT] in the even CTA
+    uint64_t* acc_full = bars + 1 + NT;         // [NT]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NT);
+
+    const uint32_t rank = cluster_ctarank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+    const int tile0 = (blockIdx.x >> 1) * NT;
+    const int n_slots = min(NT, p.n_tiles - tile0);
+    const int T = p.T;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < NT; ++s) {
+            mbar_init(&a_ready[s], 2 * EPI_WARPS);
+            mbar_init(&acc_full[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc_pair<64 * NT>(tmem_slot);
+        if (lane == 0) {
+            mbar_expect_tx(w_full, W_BWD_BYTES);
+            const uint8_t* src = p.WhhT + (long long)dir * (48 * CHUNK_G) + rank * 1024;
+            for (int c = 0; c < 48; ++c) bulk_load(w_s + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, w_full);
+        }
+        mbar_wait(w_full, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+            const uint32_t w_addr = smem_u32(w_s);
+            for (int sidx = 0; sidx < T - 1; ++sidx) {     // the result of the last reverse step is unused
+                for (int s = 0; s < n_slots; ++s) {
+                    mbar_wait_cluster(&a_ready[s], sidx & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(a_s + s * A_BWD_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 24; ++k) {
+                            const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            const uint64_t db = umma_desc_noswz(w_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            tc_mma_bf16_pair(tmem_base + s * 64, da, db, idesc, 1u);   // accumulates onto the z (.) dh carry in TMEM
+                        }
+                        tc_commit_pair(&acc_full[s]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 2 && (warp - 2) / EPI_WARPS < n_slots) {
+        const int s = (warp - 2) / EPI_WARPS;
+        const int wg = ((warp - 2) % EPI_WARPS) >> 2;
+        const int q = warp & 3;
+        const int uh = q >> 1;
+        const int rl = (q & 1) * 32 + lane;
+        const int row = rank * ROWS + rl;
+        const int tile = tile0 + s;
+        const long long b = (long long)tile * 128 + row;
+        const bool live = b < p.B;
+        const int ub = uh * 64 + wg * 32;
+        const int cb = ub / 8;                             // first of this thread's 4 chunks within the H columns
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 64 + wg * 32;
+        uint8_t* a_row = a_s + s * A_BWD_BYTES + rl * 16;
+        const uint32_t ar_remote = mapa_cluster(smem_u32(&a_ready[s]), 0);
+        const int len = (kVarLen && live) ? p.lengths[b] : T;
+        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+        // the carry z (.) dh lives in the TMEM accumulator; it starts as d_h_n
+#pragma unroll
+        for (int sc = 0; sc < 4; ++sc) {
+            uint32_t init[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) init[j] = 0u;
+            if (p.d_h_n && live) {
+                const float* src = p.d_h_n + ((long long)dir * p.B + b) * H + ub + sc * 8;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                init[0] = __float_as_uint(v0.x); init[1] = __float_as_uint(v0.y); init[2] = __float_as_uint(v0.z); init[3] = __float_as_uint(v0.w);
+                init[4] = __float_as_uint(v1.x); init[5] = __float_as_uint(v1.y); init[6] = __float_as_uint(v1.z); init[7] = __float_as_uint(v1.w);
+            }
+            tmem_st_32x32b_x8(taddr + sc * 8, init);
+        }
+        tmem_st_wait();
+
+        // raw 16-byte pieces of one chunk (8 units): r, z, n, hn (fp16), h_prev, d_out (bf16)
+        uint4 raw[6];
+        uint32_t dbits_next = 0;
+        auto load_raw = [&](int sidx, int sc) {
+            const int fstep = T - 1 - sidx;
+            const int t = dir ? (T - 1 - fstep) : fstep;
+            const int t_prev = dir ? t + 1 : t - 1;
+            const long long blk = (long long)tile * (T + 2) + t + 1;
+            const long long blk_prev = (long long)tile * (T + 2) + t_prev + 1;
+            const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(cb + sc) * CHUNK_G + row * 16;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) raw[g] = ldg16(gblk + (long long)(g * 16) * CHUNK_G);
+            raw[4] = ldg16(p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16);
+            raw[5] = p.d_out ? ldg16(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16)
+                             : make_uint4(0, 0, 0, 0);
+            if (sc == 0 && p.drop_bits)
+                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + cb));
+        };
+        load_raw(0, 0);
+        for (int sidx = 0; sidx < T; ++sidx) {             // sidx-th reverse step = forward position T-1-sidx
+            const int fstep = T - 1 - sidx;
+            const int t = dir ? (T - 1 - fstep) : fstep;
+            const long long blk = (long long)tile * (T + 2) + t + 1;
+            const bool active = !kVarLen || t < len;
+            uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 64 + cb) * CHUNK_G + row * 16;
+            const uint32_t dbits = dbits_next;
+            if (sidx > 0) {
+                mbar_wait(&acc_full[s], (sidx - 1) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int sc = 0; sc < 4; ++sc) {
+                uint32_t acc[8];
+                tmem_ld_32x32b_x8(taddr + sc * 8, acc);
+                uint4 cur[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) cur[i] = raw[i];
+                if (sc < 3) load_raw(sidx, sc + 1);
+                else if (sidx + 1 < T) load_raw(sidx + 1, 0);
+                float r[8], z[8], n[8], hn[8], hp[8], dout[8];
+                unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n); unpack8h(cur[3], hn);
+                unpack8(cur[4], hp); unpack8(cur[5], dout);
+                tmem_ld_wait();
+                float gr[8], gz[8], gn[8], ghn[8];
+                uint32_t carry[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float dov = active ? dout[j] : 0.0f;
+                    if (p.drop_bits) dov = ((dbits >> (sc * 8 + j)) & 1u) ? dov * dscale : 0.0f;
+                    const float dh = __uint_as_float(acc[j]) + dov;
+                    const float dn = dh * (1.0f - z[j]);
+                    const float dz = dh * (hp[j] - n[j]);
+                    gn[j] = dn * (1.0f - n[j] * n[j]);
+                    gz[j] = dz * z[j] * (1.0f - z[j]);
+                    ghn[j] = gn[j] * r[j];
+                    gr[j] = gn[j] * hn[j] * r[j] * (1.0f - r[j]);
+                    carry[j] = __float_as_uint(dh * z[j]);
+                }
+                const uint4 vr = pack8(gr), vz = pack8(gz), vn = pack8(gn), vh = pack8(ghn);
+                // A operand of the dh matvec: K order r | z | hn
+                *reinterpret_cast<uint4*>(a_row + (0 * 16 + cb + sc) * CHUNK_S) = vr;
+                *reinterpret_cast<uint4*>(a_row + (1 * 16 + cb + sc) * CHUNK_S) = vz;
+                *reinterpret_cast<uint4*>(a_row + (2 * 16 + cb + sc) * CHUNK_S) = vh;
+                stg16(dgblk + (long long)(0 * 16 + sc) * CHUNK_G, vr);
+                stg16(dgblk + (long long)(1 * 16 + sc) * CHUNK_G, vz);
+                stg16(dgblk + (long long)(2 * 16 + sc) * CHUNK_G, vn);
+                stg16(dgblk + (long long)(3 * 16 + sc) * CHUNK_G, vh);
+                tmem_st_32x32b_x8(taddr + sc * 8, carry);
+            }
+            tmem_st_wait();
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(ar_remote);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_pair<64 * NT>(tmem_base);
+}
+
+// (B, T, C) fp32 mask (0 or 1/keep) -> one bit per element in the order the recurrence kernels read them,
+// [tile][T][128 rows][C/8 bytes]; *scale = the non-zero value of the mask (max over all elements).
+__global__ void pack_drop_mask_kernel(const float* __restrict__ mask, int B, int T, int C, uint8_t* __restrict__ bits,
+                                      unsigned int* __restrict__ scale_bits, long long n_bytes) {
+    float mx = 0.0f;
+    const int cb = C / 8;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_bytes; e += (long long)gridDim.x * blockDim.x) {
+        const int c = e % cb;
+        const long long rt = e / cb;
+        const int row = rt & 127;
+        const long long tt = rt >> 7;
+        const int t = tt % T;
+        const long long b = (tt / T) * 128 + row;
+        unsigned int v = 0;
+        if (b < B) {
+            const float4* src = reinterpret_cast<const float4*>(mask + ((long long)b * T + t) * C + c * 8);
+            const float4 m0 = __ldg(src), m1 = __ldg(src + 1);
+            const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (m[j] != 0.0f) v |= 1u << j;
+                mx = fmaxf(mx, m[j]);
+            }
+        }
+        bits[e] = static_cast<uint8_t>(v);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(scale_bits, __float_as_uint(mx));   // positive floats order like their bits
+}
+
+// Bernoulli(keep) bits straight from a counter-based generator (no (B, T, C) float mask in HBM): the training default.
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return static_cast<uint32_t>(x);
+}
+__global__ void gen_drop_bits_kernel(uint8_t* __restrict__ bits, long long n_bytes, unsigned long long seed, uint32_t keep_thr16,
+                                     float* __restrict__ scale) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scale = 65536.0f / static_cast<float>(keep_thr16);   // 1 / (probability actually used)
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_bytes / 4; e += (long long)gridDim.x * blockDim.x) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {                     // two 16-bit uniforms per hash
+            const uint32_t h = mix32(seed + (static_cast<uint64_t>(e) << 4) + k);
+            word |= ((h & 0xffffu) < keep_thr16 ? 1u : 0u) << (2 * k);
+            word |= ((h >> 16) < keep_thr16 ? 1u : 0u) << (2 * k + 1);
+        }
+        reinterpret_cast<uint32_t*>(bits)[e] = word;
+    }
+}
+
+int rec_mode() {            // RS_REC_MODE: 0 = automatic, 1 = one CTA per tile (rec_bf16.cu), 2 = pair NT = 1, 3 = pair NT = 2
+    const char* e = getenv("RS_REC_MODE");
+    return e ? atoi(e) : 0;
+}
+
+}  // namespace
+
+namespace rs {
+
+// Tiles in flight per CTA pair, or 0 for the one-CTA-per-tile kernels of rec_bf16.cu.
+int rec_pair_nt(int B, bool need_drop) {
+    const int mode = rec_mode();
+    if (mode == 1 && !need_drop) return 0;
+    if (mode == 2) return 1;
+    if (mode == 3) return 2;
+    const int n_tiles = (B + 127) / 128;
+    return (n_tiles * 4 <= 148) ? 1 : 2;       // NT = 1 while every tile can have its own pair of SMs in both directions
+}
+
+int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
+                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int B, int T, int nt,
+                 int pf_dist, cudaStream_t stream) {
+    FwdPairParams p = {};
+    p.x = x; p.I = I;
+    p.P = static_cast<const uint8_t*>(P); p.p_block_bytes = 6LL * H * 256;
+    p.Whh = static_cast<const uint8_t*>(Whh); p.b_hn = b_hn;
+    p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
+    p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.lengths = lengths;
+    p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale; p.out_drop = static_cast<uint8_t*>(out_drop);
+    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.pf_dist = pf_dist;
+    const int pairs = (p.n_tiles + nt - 1) / nt;
+    const int smem = W_FWD_BYTES + nt * (A_FWD_BYTES + H32_BYTES) + H * 4 + 128;
+    const dim3 grid(2 * pairs, 2);
+#define RS_LAUNCH_FWD(NT_, VL_, FX_)                                                                                    \
+    do {                                                                                                                \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_pair_kernel<NT_, VL_, FX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_fwd_pair_kernel<NT_, VL_, FX_><<<grid, 64 + 256 * NT_, smem, stream>>>(p);                                  \
+    } while (0)
+#define RS_LAUNCH_FWD_X(NT_, VL_)                                                                                       \
+    do {                                                                                                                \
+        if (x) RS_LAUNCH_FWD(NT_, VL_, true); else RS_LAUNCH_FWD(NT_, VL_, false);                                      \
+    } while (0)
+    if (nt == 1) { if (lengths) RS_LAUNCH_FWD_X(1, true); else RS_LAUNCH_FWD_X(1, false); }
+    else { if (lengths) RS_LAUNCH_FWD_X(2, true); else RS_LAUNCH_FWD_X(2, false); }
+#undef RS_LAUNCH_FWD_X
+#undef RS_LAUNCH_FWD
+    count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
+                 const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T, int nt, cudaStream_t stream) {
+    BwdPairParams p = {};
+    p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
+    p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);
+    p.out = static_cast<const uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
+    p.WhhT = static_cast<const uint8_t*>(WhhT);
+    p.dG = static_cast<uint8_t*>(dG); p.dg_block_bytes = 8LL * H * 256;
+    p.lengths = lengths;
+    p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale;
+    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128;
+    const int pairs = (p.n_tiles + nt - 1) / nt;
+    const int smem = W_BWD_BYTES + nt * A_BWD_BYTES + 128;
+    const dim3 grid(2 * pairs, 2);
+#define RS_LAUNCH_BWD(NT_, VL_)                                                                                         \
+    do {                                                                                                                \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<NT_, VL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_bwd_pair_kernel<NT_, VL_><<<grid, 64 + 256 * NT_, smem, stream>>>(p);                                       \
+    } while (0)
+    if (nt == 1) { if (lengths) RS_LAUNCH_BWD(1, true); else RS_LAUNCH_BWD(1, false); }
+    else { if (lengths) RS_LAUNCH_BWD(2, true); else RS_LAUNCH_BWD(2, false); }
+#undef RS_LAUNCH_BWD
+    count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rs
+
+extern "C" int rs_pack_drop_mask(const float* mask, int B, int T, int C, void* bits, float* scale, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(mask && bits && scale && B >= 0 && T >= 0 && C > 0 && C % 32 == 0, "rs_pack_drop_mask: bad arguments (C must be a multiple of 32)");
+    RS_CUDA_OK(cudaMemsetAsync(scale, 0, sizeof(float), stream));
+    const long long n_bytes = (long long)((B + 127) / 128) * T * 128 * (C / 8);
+    if (n_bytes == 0) return 0;
+    long long blocks = (n_bytes + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_drop_mask_kernel<<<(int)blocks, 256, 0, stream>>>(mask, B, T, C, static_cast<uint8_t*>(bits),
+                                                          reinterpret_cast<unsigned int*>(scale), n_bytes);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_gen_drop_bits(void* bits, int B, int T, int C, float keep, uint64_t seed, float* scale, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rs::check_device_sm100()) return 3;
+    RS_REQUIRE(bits && scale && B >= 0 && T >= 0 && C > 0 && C % 32 == 0 && keep > 0.0f && keep <= 1.0f, "rs_gen_drop_bits: bad arguments");
+    const long long n_bytes = (long long)((B + 127) / 128) * T * 128 * (C / 8);
+    if (n_bytes == 0) return 0;
+    // keep is quantised to 16 bits; the scale is the reciprocal of the probability actually used
+    uint32_t thr = static_cast<uint32_t>(keep * 65536.0f + 0.5f);
+    if (thr > 65536u) thr = 65536u;
+    if (thr == 0u) thr = 1u;
+    long long blocks = (n_bytes / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gen_drop_bits_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<uint8_t*>(bits), n_bytes, seed, thr, scale);
+    rs::count_launch();
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+}

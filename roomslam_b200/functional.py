@@ -323,7 +323,21 @@ def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None):
     cur, padded_in, h_all = x, False, []
     if lengths is not None:
         lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+    # bf16 layers take dropout as packed bits on the PRODUCING layer (the recurrence kernel writes out (.) mask itself);
+    # the fp32 layers multiply their input by the float mask.  `mask` is either a float tensor (L-1, B, T, 2H) or, for the
+    # bf16 path, a list of (bits, scale) pairs per layer boundary.
+    bits_mode = isinstance(mask, (list, tuple))
+    if mask is not None and not bits_mode and layer_fn is not GRULayerFn:
+        from .functional_bf16 import drop_bits_from_mask
+        mask = [drop_bits_from_mask(mask[l]) for l in range(num_layers - 1)]
+        bits_mode = True
     for l in range(num_layers):
+        if bits_mode:
+            drop = mask[l] if l < num_layers - 1 else None
+            cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths, drop), None, *weights[8 * l: 8 * l + 8])
+            padded_in = True
+            h_all.append(h_n)
+            continue
         m = mask[l - 1] if (mask is not None and l > 0) else None
         cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths), m, *weights[8 * l: 8 * l + 8])
         padded_in = True

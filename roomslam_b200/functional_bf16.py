@@ -72,10 +72,39 @@ def _ones_block(device):
     return _ONES[key]
 
 
+def drop_bits_from_mask(mask: torch.Tensor):
+    """(B, T, C) fp32 dropout mask (0 or 1/keep, decision D4) -> (bits uint8 [tiles][T][128][C/8], scale (1,) fp32)."""
+    B, T, C = mask.shape
+    m = mask.contiguous().float()
+    bits = torch.empty(L.n_tiles(B), T, L.TILE, C // 8, device=m.device, dtype=torch.uint8)
+    scale = torch.empty(1, device=m.device)
+    _lib.call("rs_pack_drop_mask", _p(m), B, T, C, _p(bits), _p(scale), _stream(m))
+    return bits, scale
+
+
+def gen_drop_bits(B: int, T: int, C: int, keep: float, seed: int, device):
+    """Bernoulli(keep) dropout bits drawn on the device (no (B, T, C) float mask ever exists) -> (bits, scale)."""
+    bits = torch.empty(L.n_tiles(B), T, L.TILE, C // 8, device=device, dtype=torch.uint8)
+    scale = torch.empty(1, device=device)
+    _lib.call("rs_gen_drop_bits", _p(bits), B, T, C, float(keep), int(seed), _p(scale), torch.cuda.current_stream(device).cuda_stream)
+    return bits, scale
+
+
+def unpack_drop_bits(bits: torch.Tensor, scale: torch.Tensor, B: int) -> torch.Tensor:
+    """The (B, T, C) float mask a (bits, scale) pair stands for (tests; the oracle takes the float mask)."""
+    tiles, T, _, cb = bits.shape
+    b = bits.to(torch.int32).unsqueeze(-1) >> torch.arange(8, device=bits.device, dtype=torch.int32)
+    m = (b & 1).to(torch.float32).reshape(tiles, T, L.TILE, cb * 8) * scale
+    return m.permute(0, 2, 1, 3).reshape(tiles * L.TILE, T, cb * 8)[:B].contiguous()
+
+
 class GRULayerBF16Fn(torch.autograd.Function):
     """apply(xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r) -> (out tile-major bf16, h_n (2,B,H) fp32)
-    meta = (padded_in, B, T).  padded_in False: xin is the raw trace batch (B, T, I) fp32 (layer 0);
-    True: xin is the tile-major bf16 output of the layer below."""
+    meta = (padded_in, B, T, lengths, drop).  padded_in False: xin is the raw trace batch (B, T, I) fp32 (layer 0);
+    True: xin is the tile-major bf16 output of the layer below.  drop = None or (bits, scale) from `drop_bits_from_mask` /
+    `gen_drop_bits`: inter-layer dropout on THIS layer's output -- the returned sequence is then out (.) mask (written by
+    the recurrence kernel next to out) and backward masks the incoming gradient inside the BPTT kernel.  `mask` (the fp32
+    path's float mask on the layer INPUT) must be None here."""
 
     @staticmethod
     def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
@@ -85,6 +114,9 @@ class GRULayerBF16Fn(torch.autograd.Function):
         _need_cuda(xin, mask, w_ih, w_hh)
         padded_in, B, T = meta[:3]
         lengths = meta[3] if len(meta) > 3 else None
+        drop = meta[4] if len(meta) > 4 else None
+        if mask is not None:
+            raise _lib.RoomSlamError("GRULayerBF16Fn: pass dropout as packed bits on the producing layer (meta[4]), not as a float mask")
         if w_hh.shape[1] != H:
             raise _lib.RoomSlamError(f"bf16 mode is built for hidden_size = {H} (got {w_hh.shape[1]}); use precision='fp32'")
         dev = xin.device
@@ -108,6 +140,8 @@ class GRULayerBF16Fn(torch.autograd.Function):
             bias_x *= half_rz[None, :]
             w_ih_fwd = (w_ih_cat.view(2, 3 * H, Il) * half_rz[None, :, None]).reshape(6 * H, Il)   # forward-only copy
             out = L.empty_tm(B, T, 2 * H, dev)
+            out_drop = L.empty_tm(B, T, 2 * H, dev) if drop is not None else None
+            d_bits, d_scale = drop if drop is not None else (None, None)
             h_n = torch.empty(2, B, H, device=dev)
             gates = torch.empty(tiles, T, 2, 64, L.TILE, 8, device=dev, dtype=torch.bfloat16) if need_grad else None
             rec_flops = 2.0 * B * T * 2 * 3 * H * H
@@ -129,27 +163,29 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 xcols[:, :, 7] = bias_x - b_hi
                 whh_img = torch.cat([whh_img, xcols.to(torch.bfloat16).view(2, 3 * H, 2, 8).permute(0, 2, 1, 3)], 1).contiguous()
                 with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
-                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths), B, T, st)
+                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
+                              _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
                 saved_in = x
             else:
                 X = xin
-                if mask is not None:
-                    X = (xin * L.to_tile_major(mask)).contiguous()
                 P = torch.empty(tiles, T + 2, 6 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
                 wt = L.tile_weight_nt(w_ih_fwd)                                    # [6][Il/64][8][128][8]
                 with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
                     _nt(X, Il, [8 * k for k in range(Il // 64)], wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
                 with ktime("rec_fwd_bf16_kernel", rec_flops):
-                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths), B, T, st)
+                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
+                              _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
                 del P
                 saved_in = X
         ctx.meta = (padded_in, B, T, Il)
-        ctx.mask = mask
+        ctx.drop = drop
         ctx.lengths = lengths
         # save_for_backward (not ctx attributes): `out` is an OUTPUT of this node; holding it in a plain attribute
         # would create a reference cycle node -> out -> grad_fn -> node and keep gigabytes alive until the cycle GC runs
         ctx.save_for_backward(out, gates, saved_in, w_ih_cat, w_hh_cat)
+        if out_drop is not None:
+            return out_drop, h_n
         return out, h_n
 
     @staticmethod
@@ -170,7 +206,9 @@ class GRULayerBF16Fn(torch.autograd.Function):
             dG[:, 0].zero_()
             dG[:, T + 1].zero_()
             with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
-                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths), B, T, st)
+                d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
+                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths),
+                          _p(d_bits), _p(d_scale), B, T, st)
             # ALL weight / bias gradients of the layer in one fused pass over dG (12 roles, see csrc/gemm_blk.cu):
             #   ih roles (dir, g in r,z,n): dG block ^T . X            -> dW_ih rows, bias sums of r, z, n
             #   hh roles (dir, g in r,z,hn): dG block ^T . h(t' -/+ 1) -> dW_hh rows, bias sum of hn
@@ -219,8 +257,6 @@ class GRULayerBF16Fn(torch.autograd.Function):
                     kch = [d * 64 + g * 16 + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in (0, 1)]
                     with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
                         _nt(dG, 8 * H, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
-                    if ctx.mask is not None:
-                        dX = (dX * L.to_tile_major(ctx.mask)).contiguous()
                     d_xin = dX
         return (d_xin, None, None, dW_ih[:3 * H], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * H:], dW_hh[1], db_ih[1], db_hh[1])
 

@@ -124,12 +124,6 @@ class RoomSLAM(nn.Module):
         trace) those of a packed sequence: zero outputs past a trace's end, h_n taken at its last valid step."""
         self._check_input(x)
         lengths = self._check_lengths(x, lengths)
-        if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
-            dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
-        if dropout_mask is not None:
-            if dropout_mask.dim() == 3:
-                dropout_mask = dropout_mask.unsqueeze(0)
-            dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
         out, h_n = self._encode(x, dropout_mask, lengths)
         if isinstance(out, F_._LazyOut):
             out = out.materialize()
@@ -148,18 +142,26 @@ class RoomSLAM(nn.Module):
         bf16 = self._use_bf16(x.shape[0])
         self.decoder.precision = "bf16" if bf16 else "fp32"
         layer_fn = _bf16_layer_fn() if bf16 else F_.GRULayerFn
+        # inter-layer dropout (README.md:114): an explicit float mask (decision D4) is used as given; without one, training
+        # mode draws it -- as packed bits on the device for the bf16 kernels, as a float mask for the fp32 kernels
+        if dropout_mask is not None:
+            if dropout_mask.dim() == 3:
+                dropout_mask = dropout_mask.unsqueeze(0)
+            dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
+        elif self.training and self.dropout > 0 and self.num_layers > 1:
+            if bf16:
+                from .functional_bf16 import gen_drop_bits
+                seeds = torch.randint(0, 2 ** 62, (self.num_layers - 1,))        # host RNG: reproducible under manual_seed
+                dropout_mask = [gen_drop_bits(x.shape[0], x.shape[1], 2 * self.hidden_size, 1.0 - self.dropout, int(s), x.device)
+                                for s in seeds]
+            else:
+                dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
         return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn, lengths)
 
     def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
                 lengths: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         self._check_input(x)
         lengths = self._check_lengths(x, lengths)
-        if dropout_mask is None and self.training and self.dropout > 0 and self.num_layers > 1:
-            dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
-        if dropout_mask is not None:
-            if dropout_mask.dim() == 3:
-                dropout_mask = dropout_mask.unsqueeze(0)
-            dropout_mask = dropout_mask.to(device=x.device, dtype=torch.float32)
         _, h_n = self._encode(x, dropout_mask, lengths)
         latent = torch.cat([h_n[-2], h_n[-1]], dim=-1)          # decision D5 (README.md:115)
         return self.decoder(latent)
