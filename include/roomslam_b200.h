@@ -154,6 +154,15 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
                  const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols, const int* b_shift,
                  float* const* C, const int64_t* ldc, float* const* bias, const void* const* B2, float* const* C2,
                  int tiles, int T, void* stream);
+/* ---- bf16 mode: every bf16 operand image of one bidirectional layer from its fp32 master weights, one launch -------
+ * w: HOST array of 8 DEVICE pointers (weight_ih, weight_hh, bias_ih, bias_hh, then the _reverse twins; torch.nn.GRU's
+ * names, shapes and r|z|n gate order).  Outputs (device): whh_img [2][H/8 (+2 for layer 0)][3H][8] bf16 (the image
+ * rs_rec_fwd_bf16 documents), b_hn [2][H], bias_x [2][3H] (b_ih + b_hh of r, z; scaled like the rows), wt_proj
+ * [6H/128][I/64][8][128][8] bf16 (B pieces of rs_blk_gemm_nt for P = X W_ih^T; NULL for layer 0 whose I <= 2 columns ride
+ * in whh_img), whhT_img [2][3H/8][H][8] bf16 (rs_rec_bwd_bf16), wt_dgrad [I/128][6H/64][8][128][8] bf16 (dX = dG W_ih) or
+ * NULL. */
+int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, void* whh_img, float* b_hn, float* bias_x, void* wt_proj,
+                             void* whhT_img, void* wt_dgrad, void* stream);
 /* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
 /* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 2) fp32, its projection rides on the tensor core:
  * Whh is then [2][18][384][8] bf16 with chunk 16 = per gate row (w_hi, w_hi, w_lo) per input and (b_hi, b_lo), chunk

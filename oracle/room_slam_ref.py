@@ -120,7 +120,7 @@ class RoomSLAM(nn.Module):
 
     # -- loss (README.md:122-125; D8, D9) ----------------------------------------------------
     def compute_loss(self, pred: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        valid = target["valid"].to(torch.float32)
+        valid = target["valid"].to(pred["class_logits"].dtype)      # fp32 in use; fp64 under the oracle's own gradcheck
         nv = valid.sum().clamp_min(1.0)
         C = pred["class_logits"].shape[-1]
         ce = F.cross_entropy(pred["class_logits"].reshape(-1, C), target["classes"].reshape(-1).long(),

@@ -10,9 +10,6 @@ All arithmetic runs in hand-written CUDA behind the C ABI in include/roomslam_b2
 from .baseline import OccupancyHeatmapBaseline  # noqa: F401
 from . import synth  # noqa: F401
 
-__all__ = ["OccupancyHeatmapBaseline", "synth"]
-try:
-    from .model import RoomSLAM  # noqa: F401
-    __all__.append("RoomSLAM")
-except ImportError:  # model.py lands with the GRU kernels
-    pass
+from .model import RoomSLAM  # noqa: F401
+
+__all__ = ["OccupancyHeatmapBaseline", "RoomSLAM", "synth"]

@@ -68,3 +68,47 @@ def check(rc: int, what: str) -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(load(), name)(*args), name)
+
+
+def _cuda_device_in(obj, depth=0):
+    import torch
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.is_cuda else None
+    if depth < 2 and isinstance(obj, (list, tuple)):
+        for o in obj:
+            d = _cuda_device_in(o, depth + 1)
+            if d is not None:
+                return d
+    if depth < 2 and isinstance(obj, dict):
+        return _cuda_device_in(list(obj.values()), depth + 1)
+    return None
+
+
+def on_tensor_device(fn):
+    """Runs `fn` with the CUDA device of its first CUDA tensor argument current (also looks into lists / tuples / dicts,
+    an autograd ctx's saved tensors and an object's `.device`).  The library launches on the CURRENT device
+    (cudaGetDevice) with the tensor's stream: without this guard a model living on cuda:1 while cuda:0 is current would
+    get an invalid-resource-handle error or a launch on the wrong GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            dev = _cuda_device_in(a)
+            if dev is None and hasattr(a, "saved_tensors"):
+                try:
+                    dev = _cuda_device_in(list(a.saved_tensors))
+                except Exception:
+                    dev = None
+            if dev is None and not isinstance(a, (str, bytes)) and isinstance(getattr(a, "device", None), torch.device) \
+                    and a.device.type == "cuda":
+                dev = a.device
+            if dev is not None:
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper

@@ -153,7 +153,8 @@ ap_flags_kernel(const float* __restrict__ pred_boxes, const float* __restrict__ 
     }
     for (int m = lane; m < M; m += 32) {
         claimed[m] = 0;
-        if (gt_valid[(long long)b * M + m]) atomicAdd(&n_gt[(int)gt_labels[(long long)b * M + m]], 1);
+        const long long lab = gt_labels[(long long)b * M + m];           // a class id outside [0, NCLS) is counted nowhere
+        if (gt_valid[(long long)b * M + m] && lab >= 0 && lab < NCLS) atomicAdd(&n_gt[(int)lab], 1);
     }
     __syncwarp();
     for (int q = lane; q < Q; q += 32) {
@@ -221,7 +222,10 @@ slot_eval_kernel(const float* __restrict__ cls, const float* __restrict__ pos, c
         conf[e] = pv / den;
         label[e] = best;
         flag[e] = hit ? 1 : 0;
-        if (tv) { atomicAdd(&n_gt[tc], 1); s[0] += iou; s[1] += 1.0; s[2] += (best == tc) ? 1.0 : 0.0; }
+        if (tv) {
+            if (tc >= 0 && tc < C) atomicAdd(&n_gt[tc], 1);              // out-of-range class ids never index the counters
+            s[0] += iou; s[1] += 1.0; s[2] += (best == tc) ? 1.0 : 0.0;
+        }
         s[3] += ((pv > 0.5f) == tv) ? 1.0 : 0.0;
         s[4] += hit ? 1.0 : 0.0;
         s[5] += (pv > 0.5f) ? 1.0 : 0.0;

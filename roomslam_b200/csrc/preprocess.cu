@@ -61,6 +61,11 @@ trace_features_kernel(const float4* __restrict__ pts, const long long* __restric
                 if (N > max_len) {
                     const double step = __ddiv_rn((double)(N - 1), (double)(max_len - 1));
                     i = (j == max_len - 1) ? (N - 1) : (long long)__dmul_rn((double)j, step);
+                    // time order must hold over ALL source points, not only the kept rows (the reference argsorts before it
+                    // differences and down-samples, inference.py:38-39): this thread checks the points skipped since row j - 1
+                    const long long ip = j == 0 ? 0 : (long long)__dmul_rn((double)(j - 1), step);
+                    for (long long k = ip + 1; k < i; ++k)
+                        if (__ldg(pts + o0 + k).w < __ldg(pts + o0 + k - 1).w) *unsorted_flag = 1;
                 }
                 const float t0 = __ldg(pts + o0).w;
                 const P4 a = load_norm(pts, o0 + i, t0);

@@ -86,6 +86,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_fwd_bf16_kernel(const FwdP
     rs::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // pad rows t' = 0 and T + 1 of this tile: the time-shifted weight-gradient GEMM reads them as h = 0
+    for (int i = threadIdx.x; i < 2 * 16 * 128; i += NUM_THREADS) {
+        const int r = i & 127, c = (i >> 7) & 15, pad = i >> 11;
+        stg16(p.out + ((long long)tile * (T + 2) + (pad ? T + 1 : 0)) * p.out_block_bytes + (long long)(dir * 16 + c) * CHUNK + r * 16,
+              make_uint4(0, 0, 0, 0));
+    }
+
     if (warp == 0) {
         // ===================== W loader + MMA issuer =====================
         const uint32_t w_bytes = fused_x ? (W_BYTES + WX_BYTES) : W_BYTES;
@@ -284,6 +291,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rec_bwd_bf16_kernel(const BwdP
     __syncthreads();
     rs::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    for (int i = threadIdx.x; i < 2 * 64 * 128; i += NUM_THREADS) {      // pad rows of dG
+        const int r = i & 127, c = (i >> 7) & 63, pad = i >> 13;
+        stg16(p.dG + ((long long)tile * (T + 2) + (pad ? T + 1 : 0)) * p.dg_block_bytes + (long long)(dir * 64 + c) * CHUNK + r * 16,
+              make_uint4(0, 0, 0, 0));
+    }
 
     if (warp == 0) {
         if (lane == 0) {

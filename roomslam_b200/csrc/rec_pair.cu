@@ -110,6 +110,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // pad rows t' = 0 and T + 1 of this CTA's rows: the time-shifted weight-gradient GEMM reads them as h = 0
+    for (int i = threadIdx.x; i < n_slots * 2 * 16 * ROWS; i += blockDim.x) {
+        const int rl = i % ROWS, c = (i / ROWS) % 16, pad = (i / (ROWS * 16)) % 2, s = i / (ROWS * 32);
+        const long long off = ((long long)(tile0 + s) * (T + 2) + (pad ? T + 1 : 0)) * p.out_block_bytes
+                              + (long long)(dir * 16 + c) * CHUNK_G + (rank * ROWS + rl) * 16;
+        stg16(p.out + off, make_uint4(0, 0, 0, 0));
+        if (p.out_drop) stg16(p.out_drop + off, make_uint4(0, 0, 0, 0));
+    }
+
     if (warp == 0) {
         if (rank == 0) {
             // ===================== MMA issuer for the pair =====================
@@ -326,6 +335,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // pad rows of dG (the weight / data gradient GEMMs run over all T + 2 rows of a tile)
+    for (int i = threadIdx.x; i < n_slots * 2 * 64 * ROWS; i += blockDim.x) {
+        const int rl = i % ROWS, c = (i / ROWS) % 64, pad = (i / (ROWS * 64)) % 2, s = i / (ROWS * 128);
+        const long long off = ((long long)(tile0 + s) * (T + 2) + (pad ? T + 1 : 0)) * p.dg_block_bytes
+                              + (long long)(dir * 64 + c) * CHUNK_G + (rank * ROWS + rl) * 16;
+        stg16(p.dG + off, make_uint4(0, 0, 0, 0));
+    }
 
     if (warp == 0) {
         if (rank == 0) {

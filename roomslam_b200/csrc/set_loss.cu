@@ -19,6 +19,9 @@ namespace {
 
 constexpr int MAXQ = 128, MAXM = 64, MAXN = 128;      // queries, collider slots, max(Q, M)
 constexpr int NCLS = 4;
+// Class ids index the NCLS logits of a query: an id outside [0, NCLS) (upstream's CrossEntropyLoss would raise) is clamped
+// so that it can never read or write out of bounds.
+__device__ __forceinline__ int clamp_label(long long l) { return l < 0 ? 0 : (l >= NCLS ? NCLS - 1 : (int)l); }
 
 __device__ __forceinline__ float class_prob(const float* l, int c) {
     const float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
@@ -62,7 +65,7 @@ hungarian_match_kernel(const float* __restrict__ pred_boxes, const float* __rest
         float d = 0.0f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) d = __fadd_rn(d, fabsf(__fsub_rn(pb[k], gb[k])));
-        const float p = class_prob(pred_logits + ((long long)b * Q + q) * NCLS, (int)gt_labels[(long long)b * M + m]);
+        const float p = class_prob(pred_logits + ((long long)b * Q + q) * NCLS, clamp_label(gt_labels[(long long)b * M + m]));
         cost[e] = __fadd_rn(__fmul_rn(w_class, -p), __fmul_rn(w_box, d));
     }
     const bool transposed = Mv < Q;                       // rows = the smaller side
@@ -171,7 +174,7 @@ set_loss_pairs_kernel(const float* __restrict__ pred_boxes, const float* __restr
         const float* l = pred_logits + ((long long)b * Q + q) * NCLS;
         const float* pb = pred_boxes + ((long long)b * Q + q) * 6;
         const float* gb = gt_boxes + ((long long)b * M + m) * 6;
-        const int label = (int)gt_labels[(long long)b * M + m];
+        const int label = clamp_label(gt_labels[(long long)b * M + m]);
         {   // cross-entropy of the matched query against its collider's label
             const float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
             float ex[NCLS], s = 0.0f;

@@ -22,6 +22,7 @@ class MetricAccumulator:
         self.counts = torch.zeros(7, dtype=torch.float64, device=device)
         self.iou_thresh = float(iou_thresh)
 
+    @_lib.on_tensor_device
     def update(self, outputs: Dict[str, torch.Tensor], targets: Dict[str, torch.Tensor]) -> None:
         pb = outputs["pred_boxes"].detach().contiguous().float()
         pc = outputs["pred_classes"].detach().contiguous().float()
@@ -56,6 +57,7 @@ def evaluate_metrics(model, dataloader, device, iou_thresh: float = 0.5) -> Dict
     return acc.compute()
 
 
+@_lib.on_tensor_device
 def nms_batch(boxes: torch.Tensor, classes: torch.Tensor, confidence_threshold: float = 0.7, nms_threshold: float = 0.3):
     """boxes [B,Q,6], classes [B,Q,4] logits -> (keep_idx [B,Q] int32 (-1 padded, reference output order), n_keep [B],
     confidence [B,Q], label [B,Q])."""
@@ -84,6 +86,7 @@ def post_process_predictions(boxes: torch.Tensor, classes: torch.Tensor, confide
             for i in idx.tolist()]
 
 
+@_lib.on_tensor_device
 def ap_flags(boxes, classes, gt_boxes, gt_labels, gt_valid, iou_thresh: float = 0.5):
     """-> (confidence [B,Q], label [B,Q], tp_flag [B,Q], colliders per class [4]) on the device."""
     pb, pc = boxes.detach().contiguous().float(), classes.detach().contiguous().float()
@@ -144,6 +147,7 @@ class SlotEvaluator:
         self.n_slots = 0
         self._conf, self._label, self._flag = [], [], []
 
+    @_lib.on_tensor_device
     def update(self, pred: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> None:
         cl = pred["class_logits"].detach().contiguous().float()
         B, N, C = cl.shape

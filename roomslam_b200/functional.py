@@ -178,6 +178,7 @@ class GRULayerFn(torch.autograd.Function):
     backward-through-time of the layer below is still running."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         # unused outputs (the top layer's sequence output feeds nothing: only h_n reaches the decoder) must arrive in
         # backward as None, not as a materialised 2 GB tensor of zeros that is then filled, converted and read back
@@ -240,6 +241,7 @@ class GRULayerFn(torch.autograd.Function):
         return out, h_n
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_out, d_h_n):
         B, T, Il, H = ctx.dims
         out, gates, xin, w_ih_cat, w_hh_cat = ctx.saved_tensors
@@ -365,6 +367,7 @@ class DecoderFn(torch.autograd.Function):
     apply(latent, N, C, W1, b1, W2, b2, Wc, bc, Wp, bp, Ws, bs, Wo, bo, Wv, bv) -> 5 prediction tensors."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, latent, N, C, W1, b1, W2, b2, *heads):
         _need_cuda(latent, W1, W2, *heads)
         latent = latent.contiguous().float()
@@ -392,6 +395,7 @@ class DecoderFn(torch.autograd.Function):
         return cls, pos, size, orient, valid
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_cls, d_pos, d_size, d_orient, d_valid):
         latent, W1, W2, Wh, f1, f2, raw = ctx.saved_tensors
         B, N, C = ctx.dims
@@ -438,6 +442,7 @@ class MultiTaskLossFn(torch.autograd.Function):
     = [total, class, position, size, orientation, validity] (README.md:122-125, weights D9)."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, cls, pos, size, orient, vlogit, t_cls, t_pos, t_size, t_orient, t_valid):
         _need_cuda(cls, pos, size, orient, vlogit, t_cls, t_pos, t_size, t_orient, t_valid)
         B, N, C = cls.shape
@@ -457,6 +462,7 @@ class MultiTaskLossFn(torch.autograd.Function):
         return losses
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_losses):
         sums, *g = ctx.saved_tensors
         B, N, C = ctx.dims

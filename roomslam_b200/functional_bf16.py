@@ -72,6 +72,7 @@ def _ones_block(device):
     return _ONES[key]
 
 
+@_lib.on_tensor_device
 def drop_bits_from_mask(mask: torch.Tensor):
     """(B, T, C) fp32 dropout mask (0 or 1/keep, decision D4) -> (bits uint8 [tiles][T][128][C/8], scale (1,) fp32)."""
     B, T, C = mask.shape
@@ -86,7 +87,8 @@ def gen_drop_bits(B: int, T: int, C: int, keep: float, seed: int, device):
     """Bernoulli(keep) dropout bits drawn on the device (no (B, T, C) float mask ever exists) -> (bits, scale)."""
     bits = torch.empty(L.n_tiles(B), T, L.TILE, C // 8, device=device, dtype=torch.uint8)
     scale = torch.empty(1, device=device)
-    _lib.call("rs_gen_drop_bits", _p(bits), B, T, C, float(keep), int(seed), _p(scale), torch.cuda.current_stream(device).cuda_stream)
+    with torch.cuda.device(bits.device):
+        _lib.call("rs_gen_drop_bits", _p(bits), B, T, C, float(keep), int(seed), _p(scale), _stream(bits))
     return bits, scale
 
 
@@ -107,6 +109,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
     path's float mask on the layer INPUT) must be None here."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         # unused outputs (the top layer's sequence output feeds nothing: only h_n reaches the decoder) must arrive in
         # backward as None, not as a materialised 2 GB tensor of zeros that is then filled, converted and read back
@@ -125,43 +128,33 @@ class GRULayerBF16Fn(torch.autograd.Function):
         tiles = L.n_tiles(B)
         Il = w_ih.shape[1]
         with torch.no_grad():
-            w_ih_cat = torch.cat([w_ih, w_ih_r], 0).float()                       # [6H, Il]
-            w_hh_cat = torch.stack([w_hh, w_hh_r], 0).float()                     # [2, 3H, H]
-            # sigma(a) = 1/2 tanh(a/2) + 1/2: the kernel evaluates tanh(acc + p) directly, so the r and z rows of W_hh,
-            # W_ih and the biases carry the factor 1/2 (an exact power-of-two scaling, no extra rounding)
-            half_rz = torch.ones(3 * H, device=dev)
-            half_rz[:2 * H] = 0.5
-            whh_img = (w_hh_cat * half_rz[None, :, None]).to(torch.bfloat16).view(2, 3 * H, H // 8, 8) \
-                .permute(0, 2, 1, 3).contiguous()
-            b_hn = torch.stack([b_hh[2 * H:], b_hh_r[2 * H:]], 0).float().contiguous()
-            bias_x = torch.stack([b_ih, b_ih_r], 0).float().clone()               # [2, 3H]
-            bias_x[0, :2 * H] += b_hh[:2 * H]
-            bias_x[1, :2 * H] += b_hh_r[:2 * H]
-            bias_x *= half_rz[None, :]
-            w_ih_fwd = (w_ih_cat.view(2, 3 * H, Il) * half_rz[None, :, None]).reshape(6 * H, Il)   # forward-only copy
-            out = L.empty_tm(B, T, 2 * H, dev)
-            out_drop = L.empty_tm(B, T, 2 * H, dev) if drop is not None else None
+            # every bf16 operand image of the layer (forward AND backward) in one launch, from the fp32 master weights
+            ws = [t.detach().float().contiguous() for t in (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
+            bf = torch.bfloat16
+            need_dx = padded_in and ctx.needs_input_grad[0]
+            whh_img = torch.empty(2, H // 8 + (0 if padded_in else 2), 3 * H, 8, device=dev, dtype=bf)
+            b_hn = torch.empty(2, H, device=dev)
+            bias_x = torch.empty(2, 3 * H, device=dev)
+            wt = torch.empty(6 * H // 128, Il // 64, 8, L.TILE, 8, device=dev, dtype=bf) if padded_in else None
+            whhT_img = torch.empty(2, 3 * H // 8, H, 8, device=dev, dtype=bf)
+            wt_dgrad = torch.empty(Il // 128, 6 * H // 64, 8, L.TILE, 8, device=dev, dtype=bf) if need_dx else None
+            if not padded_in and Il > 2:
+                raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 2")
+            if padded_in and Il != 2 * H:
+                raise _lib.RoomSlamError("bf16 mode: deeper layers take the 2H-column output of the layer below")
+            wp = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in ws])
+            _lib.call("rs_gru_pack_weights_bf16", ctypes.addressof(wp), H, Il, _p(whh_img), _p(b_hn), _p(bias_x), _p(wt), _p(whhT_img),
+                      _p(wt_dgrad), st)
+            # (the recurrence kernels zero the pad rows t' = 0, T + 1 of what they write)
+            out = L.empty_tm(B, T, 2 * H, dev, zero_pads=False)
+            out_drop = L.empty_tm(B, T, 2 * H, dev, zero_pads=False) if drop is not None else None
             d_bits, d_scale = drop if drop is not None else (None, None)
             h_n = torch.empty(2, B, H, device=dev)
             gates = torch.empty(tiles, T, 2, 64, L.TILE, 8, device=dev, dtype=torch.bfloat16) if need_grad else None
             rec_flops = 2.0 * B * T * 2 * 3 * H * H
             X = None
             if not padded_in:
-                if Il > 2:
-                    raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 2")
                 x = xin.contiguous().float()
-                # input rows of the weight image: (w_hi, w_hi, w_lo) per input and (b_hi, b_lo); see csrc/rec_bf16.cu
-                wv = w_ih_fwd.view(2, 3 * H, Il)
-                w_hi = wv.to(torch.bfloat16).float()
-                b_hi = bias_x.to(torch.bfloat16).float()
-                xcols = torch.zeros(2, 3 * H, 16, device=dev)
-                for c in range(Il):
-                    xcols[:, :, 3 * c] = w_hi[:, :, c]
-                    xcols[:, :, 3 * c + 1] = w_hi[:, :, c]
-                    xcols[:, :, 3 * c + 2] = wv[:, :, c] - w_hi[:, :, c]
-                xcols[:, :, 6] = b_hi
-                xcols[:, :, 7] = bias_x - b_hi
-                whh_img = torch.cat([whh_img, xcols.to(torch.bfloat16).view(2, 3 * H, 2, 8).permute(0, 2, 1, 3)], 1).contiguous()
                 with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
                     _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
                               _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
@@ -169,7 +162,6 @@ class GRULayerBF16Fn(torch.autograd.Function):
             else:
                 X = xin
                 P = torch.empty(tiles, T + 2, 6 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
-                wt = L.tile_weight_nt(w_ih_fwd)                                    # [6][Il/64][8][128][8]
                 with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
                     _nt(X, Il, [8 * k for k in range(Il // 64)], wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
@@ -183,15 +175,16 @@ class GRULayerBF16Fn(torch.autograd.Function):
         ctx.lengths = lengths
         # save_for_backward (not ctx attributes): `out` is an OUTPUT of this node; holding it in a plain attribute
         # would create a reference cycle node -> out -> grad_fn -> node and keep gigabytes alive until the cycle GC runs
-        ctx.save_for_backward(out, gates, saved_in, w_ih_cat, w_hh_cat)
+        ctx.save_for_backward(out, gates, saved_in, whhT_img, wt_dgrad)
         if out_drop is not None:
             return out_drop, h_n
         return out, h_n
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_out, d_h_n):
         padded_in, B, T, Il = ctx.meta
-        out, gates, saved_in, w_ih_cat, w_hh_cat = ctx.saved_tensors
+        out, gates, saved_in, whhT_img, wt_dgrad = ctx.saved_tensors
         if gates is None:
             raise RuntimeError("GRULayerBF16Fn: forward ran without saving activations (nothing required grad)")
         dev = out.device
@@ -200,11 +193,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
         with torch.no_grad():
             d_out = d_out.contiguous().to(torch.bfloat16) if d_out is not None else None
             d_h_n = d_h_n.contiguous().float() if d_h_n is not None else None
-            whhT_img = w_hh_cat.transpose(1, 2).to(torch.bfloat16).contiguous().view(2, H, 3 * H // 8, 8) \
-                .permute(0, 2, 1, 3).contiguous()                                  # [2][48][128][8]
             dG = torch.empty(tiles, T + 2, 8 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
-            dG[:, 0].zero_()
-            dG[:, T + 1].zero_()
             with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
                 d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
                 _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths),
@@ -231,8 +220,6 @@ class GRULayerBF16Fn(torch.autograd.Function):
             else:
                 # deeper layers: 12 roles: ih (N = 2H) and hh (N = H) per gate block.  (18 equal-weight N = H roles were
                 # tried to keep the roles in lockstep for L2 sharing: slower, 6.1 ms vs 5.5 ms - more L2->SM traffic.)
-                if Il != 2 * H:
-                    raise _lib.RoomSlamError("bf16 mode: deeper layers take the 2H-column output of the layer below")
                 dW_ih_buf = torch.zeros(6 * H, Il, device=dev)
                 for d in (0, 1):
                     sh = -1 if d == 0 else 1
@@ -253,7 +240,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 X = saved_in
                 if ctx.needs_input_grad[0]:
                     dX = torch.empty(tiles, T + 2, Il // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
-                    wt = L.tile_weight_nt(w_ih_cat.t().contiguous())               # [Il/128][12][8][128][8]
+                    wt = wt_dgrad                                                  # [Il/128][12][8][128][8]
                     kch = [d * 64 + g * 16 + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in (0, 1)]
                     with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
                         _nt(dG, 8 * H, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
@@ -284,6 +271,7 @@ class DecoderBF16Fn(torch.autograd.Function):
     outputs (logits, positions, ...) leave the last GEMM in fp32.  Same signature as functional.DecoderFn."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, latent, N, C, W1, b1, W2, b2, *heads):
         _need_cuda(latent, W1, W2, *heads)
         B = latent.shape[0]
@@ -319,6 +307,7 @@ class DecoderBF16Fn(torch.autograd.Function):
         return cls, pos, size, orient, valid
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_cls, d_pos, d_size, d_orient, d_valid):
         lat, W1b, W2b, Wh, f1, f2, raw = ctx.saved_tensors
         B, N, C, NH, NHp = ctx.dims

@@ -28,6 +28,7 @@ class LinearFn(torch.autograd.Function):
     """y[M, N] = x[M, K] @ w[N, K]^T + b.  Large M: bf16x6 tensor-core GEMMs; otherwise rs_sgemm.  Bias gradient: rs_colsum_f32."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, x, w, b, allow_tc=False):
         _need_cuda(x, w, b)
         x, w = x.contiguous().float(), w.contiguous().float()
@@ -48,6 +49,7 @@ class LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous().float()
@@ -94,6 +96,7 @@ class LSTMLayerFn(torch.autograd.Function):
         -> out (B, T+2, 2H) padded (pad rows zero).  Replaces one layer of torch.nn.LSTM (model.py:16-23)."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, xin, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         _need_cuda(xin, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         xin = xin.contiguous().float()
@@ -131,6 +134,7 @@ class LSTMLayerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_out):
         B, T, I, H = ctx.dims
         out, saved, xin, w_ih_cat, w_hh_cat = ctx.saved_tensors
@@ -192,6 +196,7 @@ class QueryAttnFn(torch.autograd.Function):
     traces / mask / mean / rms / count are data (no gradient)."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx_, memory, qk, qb, traces, mask_u8, mean, rms, count):
         _need_cuda(memory, qk, qb, traces, mask_u8, mean, rms, count)
         memory, qk, qb = memory.contiguous().float(), qk.contiguous().float(), qb.contiguous().float()
@@ -212,6 +217,7 @@ class QueryAttnFn(torch.autograd.Function):
         return ctx, anchor, summary
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx_, d_ctx, d_anchor, d_summary):
         memory, qk, qb, traces, mask_u8, mean, rms, count, ctx, anchor, stats = ctx_.saved_tensors
         B, Np, D = memory.shape
@@ -232,6 +238,7 @@ class QueryAttnFn(torch.autograd.Function):
         return d_mem, dq[:, :D].contiguous(), dq[:, D].contiguous(), None, None, None, None, None
 
 
+@_lib.on_tensor_device
 def trace_stats(traces: torch.Tensor, mask_u8: Optional[torch.Tensor]):
     """Per-trace (mean (B,3), rms (B,), count (B,)) of model.py:38-46 in one launch."""
     B, N, Fdim = traces.shape

@@ -39,6 +39,7 @@ def sort_by_time(packed: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
     return packed[order].contiguous()
 
 
+@_lib.on_tensor_device
 def trace_features(traces, offsets: torch.Tensor | None = None, max_len: int = 3000, sort="auto",
                    check_sorted: bool = False) -> dict:
     """traces: list of (N_i, 4) arrays, or a packed (total, 4) CUDA tensor with `offsets` (B+1 int64).

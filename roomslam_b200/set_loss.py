@@ -14,6 +14,7 @@ from . import _lib
 from .functional import _need_cuda, _p, _stream
 
 
+@_lib.on_tensor_device
 def hungarian_match(pred_boxes, pred_classes, gt_boxes, gt_labels, gt_valid_mask, cost_class=1.0, cost_box=5.0):
     """-> (match_pred [B,K], match_slot [B,K], match_rank [B,K], n_match [B]) int32 CUDA tensors, K = min(Q, M), -1 padded."""
     _need_cuda(pred_boxes, pred_classes, gt_boxes, gt_labels, gt_valid_mask)
@@ -55,6 +56,7 @@ class SetLossFn(torch.autograd.Function):
     """(pred_boxes, pred_classes) + targets + matches -> losses [4] = (class, l1, giou, weighted total)."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, pred_boxes, pred_classes, gt_boxes, gt_labels, mp, ms, n, weights):
         B, Q = pred_boxes.shape[:2]
         M = gt_boxes.shape[1]
@@ -72,6 +74,7 @@ class SetLossFn(torch.autograd.Function):
         return losses
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, d_losses):
         g_logits, g_l1, g_giou = ctx.saved_tensors
         wc, wl, wg = ctx.weights

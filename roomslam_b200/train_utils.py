@@ -6,6 +6,7 @@ clip_grad_norm_(1.0), optimizer.step with AdamW :440-444), for one process per G
 """
 from __future__ import annotations
 
+import re
 from typing import List, Optional
 
 import torch
@@ -66,8 +67,12 @@ def default_bucket(name: str) -> int:
     if name.startswith("decoder."):
         return 0
     if name.startswith("encoder."):
-        layer = int(name.split("_l")[1].split("_")[0])
-        return 1000 - layer          # higher layers earlier
+        m = re.search(r"_l(\d+)", name)
+        if m:
+            return 1000 - int(m.group(1))          # higher layers earlier
+        # the BiLSTM pipeline's encoder (lstm_model.py): out_proj is the last module of the forward pass, so its gradient
+        # is final first; input_proj feeds layer 0 and finishes last
+        return 500 if "out_proj" in name else 1500
     return 2000
 
 
@@ -145,9 +150,10 @@ class FusedAdamW:
             raise _lib.RoomSlamError("FusedAdamW runs on CUDA only (no CPU fallback)")
         self.t += 1
         f = self.flat
-        _lib.call("rs_adamw_step_f32", f.flat.data_ptr(), f.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), f.numel,
-                  self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t, grad_scale, self.max_norm or 0.0,
-                  self.scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.device(f.flat.device):
+            _lib.call("rs_adamw_step_f32", f.flat.data_ptr(), f.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), f.numel,
+                      self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t, grad_scale, self.max_norm or 0.0,
+                      self.scratch.data_ptr(), torch.cuda.current_stream(f.flat.device).cuda_stream)
 
 
 class HostBatchPrefetcher:

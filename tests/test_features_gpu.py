@@ -73,6 +73,25 @@ def test_unsorted_input_is_flagged():
     preprocess.trace_features([pts], sort=True, check_sorted=True)
 
 
+def test_long_unsorted_trace_is_detected_between_kept_rows():
+    """A trace LONGER than max_len whose only out-of-order timestamps sit between two kept (down-sampled) rows: the
+    default sort="auto" must still sort it (the reference always argsorts, inference.py:38-39) and check_sorted must raise."""
+    from roomslam_b200 import preprocess
+    rng = np.random.default_rng(11)
+    n, cap = 5000, 100
+    t = np.cumsum(rng.uniform(0.01, 0.1, n)) + 7.0
+    pts = np.stack([rng.normal(0, 3, n), rng.normal(1.6, 0.1, n), rng.normal(0, 3, n), t], 1).astype(np.float32)
+    kept = set(features_ref.downsample_index(n, cap).tolist())
+    k = next(i for i in range(1000, n - 3) if not ({i - 1, i, i + 1, i + 2} & kept))
+    pts[[k, k + 1]] = pts[[k + 1, k]]                       # one swapped pair, neither row nor its neighbours is kept
+    with pytest.raises(ValueError):
+        preprocess.trace_features([pts], max_len=cap, sort=False, check_sorted=True)
+    auto = preprocess.trace_features([pts, pts[:50]], max_len=cap)
+    want, wmask = features_ref.collate([features_ref.process_points(pts, cap), features_ref.process_points(pts[:50], cap)])
+    assert np.array_equal(bits(auto["traces"].cpu().numpy()), bits(want))
+    assert np.array_equal(auto["trace_mask"].cpu().numpy(), wmask)
+
+
 def test_large_batch_property():
     """Full-size property: 4096 traces x 3000 points; speed^2 == |v|^2 and a == diff(v) recomputed in torch."""
     from roomslam_b200 import preprocess

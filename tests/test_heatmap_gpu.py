@@ -108,3 +108,42 @@ def test_large_config_properties_and_c_oracle():
     b.bin_into(pts[: n // 2], occ2, stat2, d2, accumulate=True)
     b.bin_into(pts[n // 2:], occ2, stat2, d2, accumulate=True)
     assert torch.equal(occ2, occ) and torch.equal(stat2, stat) and int(d2.item()) == nd
+
+
+def test_property_random_rooms_cuda_equals_oracles():
+    """Hypothesis property test: random bounds / resolutions / stationary speeds, points on
+    cell edges, outside the room, NaN, +-Inf, denormals, T = 1, ragged batch sizes: CUDA == numpy oracle == C oracle,
+    every point is binned or dropped, and a stationary sample is also a visit."""
+    from hypothesis import given, settings, strategies as st
+    finite = st.floats(min_value=-40.0, max_value=40.0, allow_nan=False, width=32)
+    weird = st.sampled_from([float("nan"), float("inf"), float("-inf"), 0.0, -0.0, 1e-30, -1e-30, 3.0e38])
+
+    @settings(max_examples=40, deadline=None)
+    @given(x_min=st.floats(-20, 5), y_min=st.floats(-20, 5), w=st.floats(0.25, 12), h=st.floats(0.25, 12),
+           res=st.sampled_from([0.05, 0.1, 0.013, 0.25, 1.0]), v=st.sampled_from([0.1, 0.5, 0.01]),
+           n=st.sampled_from([1, 3, 31, 32, 33, 130]), t=st.sampled_from([1, 2, 7, 8, 16, 50]), seed=st.integers(0, 2 ** 31 - 1),
+           specials=st.lists(st.tuples(st.integers(0, 129), st.integers(0, 49), st.one_of(weird, finite), st.one_of(weird, finite)), max_size=8),
+           on_edges=st.booleans(), variant=st.sampled_from(VARIANTS))
+    def check(x_min, y_min, w, h, res, v, n, t, seed, specials, on_edges, variant):
+        kw = dict(bounds=(x_min, x_min + w, y_min, y_min + h), resolution=res, stationary_speed=v)
+        ref = baseline_ref.OccupancyHeatmapBaseline(**kw)
+        if variant in (1, 2, 4, 5) and (t % 2 or ref.gx * ref.gy > 40960):
+            variant = 0
+        rng = np.random.default_rng(seed)
+        pts = np.stack([rng.uniform(x_min - 1, x_min + w + 1, (n, t)), rng.uniform(y_min - 1, y_min + h + 1, (n, t))], -1).astype(np.float32)
+        if on_edges:
+            k = rng.integers(0, max(1, ref.gx), (n, t))
+            pts[..., 0] = (np.float32(x_min) + k.astype(np.float32) * np.float32(res)).astype(np.float32)
+            if t > 1:
+                pts[:, 1:] = np.where(rng.random((n, t - 1, 1)) < 0.5, pts[:, :-1], pts[:, 1:])      # repeated points: stationary
+        for (i, j, px, py) in specials:
+            if i < n and j < t:
+                pts[i, j] = (px, py)
+        o_np = baseline_ref.bin_points(pts, ref.bounds[0], ref.bounds[2], ref.resolution, ref.gx, ref.gy, ref.thr2)
+        o_c = heatmap_ref_c.bin_points(pts, ref.bounds[0], ref.bounds[2], ref.resolution, ref.gx, ref.gy, ref.thr2)
+        occ, stat, nd = _gpu_bin(pts, variant, **kw)
+        assert np.array_equal(occ, o_np[0]) and np.array_equal(stat, o_np[1]) and nd == o_np[2]
+        assert np.array_equal(occ, o_c[0]) and np.array_equal(stat, o_c[1]) and nd == o_c[2]
+        assert int(occ.sum()) + nd == n * t and (stat <= occ).all()
+
+    check()
