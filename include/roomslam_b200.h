@@ -160,9 +160,12 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
  * rs_rec_fwd_bf16 documents), b_hn [2][H], bias_x [2][3H] (b_ih + b_hh of r, z; scaled like the rows), wt_proj
  * [6H/128][I/64][8][128][8] bf16 (B pieces of rs_blk_gemm_nt for P = X W_ih^T; NULL for layer 0 whose I <= 2 columns ride
  * in whh_img), whhT_img [2][3H/8][H][8] bf16 (rs_rec_bwd_bf16), wt_dgrad [I/128][6H/64][8][128][8] bf16 (dX = dG W_ih) or
- * NULL. */
-int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, void* whh_img, float* b_hn, float* bias_x, void* wt_proj,
-                             void* whhT_img, void* wt_dgrad, void* stream);
+ * NULL.
+ * split = 1: every weight image holds a bf16 PAIR per weight, hi = bf16(w) then lo = bf16(w - hi), stacked along K
+ * (whh_img: chunks [0, H/8) hi, [H/8, H/4) lo, then the layer-0 input chunks; whhT_img, wt_proj, wt_dgrad: K blocks hi
+ * then lo); rs_rec_fwd_bf16 / rs_rec_bwd_bf16 take the same flag, rs_blk_gemm_nt simply runs the longer K. */
+int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, int split, void* whh_img, float* b_hn, float* bias_x,
+                             void* wt_proj, void* whhT_img, void* wt_dgrad, void* stream);
 /* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
 /* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 2) fp32, its projection rides on the tensor core:
  * Whh is then [2][18][384][8] bf16 with chunk 16 = per gate row (w_hi, w_hi, w_lo) per input and (b_hi, b_lo), chunk
@@ -171,13 +174,14 @@ int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, void* whh_img,
  * zero pad rows), gates [tiles][T][2][64][128][8] fp16 (NULL for inference), h_n [2][B][H] fp32. */
 int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
                     void* gates, float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale,
-                    void* out_drop, int B, int T, void* stream);
+                    void* out_drop, int split, int B, int T, void* stream);
 /* x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (zero padded): layer-0 input for rs_blk_wgrad. */
 int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 /* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
  * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                    const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T, void* stream);
+                    const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T,
+                    void* stream);
 /* Inter-layer dropout (README.md:114; analogue src/benchmark/model.py:13,20) without a (B, T, 2H) multiply in HBM: the
  * mask travels as ONE BIT per element, [tiles][T][128 rows][C/8 bytes] (C = 2H), plus a device scalar scale = 1/keep.
  * rs_rec_fwd_bf16 with drop_bits writes out_drop = out (.) mask * scale next to out (the next layer's input);

@@ -10,7 +10,7 @@ import re
 from typing import Dict, List, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libroomslam_b200.so")
+LIB_PATH = os.environ.get("RS_LIB") or os.path.join(_HERE, "libroomslam_b200.so")    # RS_LIB: experiment builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "roomslam_b200.h")
 
 _C2CT = {

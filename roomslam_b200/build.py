@@ -12,8 +12,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "libroomslam_b200.so")
+OBJ = os.path.join(CSRC, "_obj" + os.environ.get("RS_LIB_SUFFIX", ""))
+# experiments: RS_NVCC_DEFS="-DFOO -DBAR" builds a variant into libroomslam_b200<RS_LIB_SUFFIX>.so with its own object
+# directory; RS_LIB=<path> makes _lib.py load it.  The product build sets neither.
+_SUFFIX = os.environ.get("RS_LIB_SUFFIX", "")
+LIB = os.path.join(HERE, f"libroomslam_b200{_SUFFIX}.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -42,7 +45,8 @@ def _deps_mtime() -> float:
 
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc(), *ARCH, *COMMON, *EXTRA.get(src, []), *os.environ.get("RS_NVCC_DEFS", "").split(), "-c",
+           os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

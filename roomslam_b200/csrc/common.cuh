@@ -286,21 +286,14 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t ra
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Arrival on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope), as CUTLASS's 2-SM
+// kernels use: what the arrival publishes here are this CTA's OWN shared-memory writes, already fenced into the async
+// proxy, for this SM's own tensor core.  A cluster-scope release compiles to MEMBAR.ALL.GPU + CCTL.IVALL, which waits
+// for every global store of the step (~1000 cycles on the per-step critical path, ncu: stall_membar).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {      // the same warp of BOTH CTAs executes this
     static_assert(kCols >= 32 && kCols <= 512 && (kCols & (kCols - 1)) == 0, "TMEM columns: power of two in [32,512]");

@@ -24,7 +24,7 @@ namespace {
 constexpr int CHUNK_BYTES = 2048;          // one 16-byte column chunk of a 128-trace block
 constexpr int PIECE_BYTES = 8 * CHUNK_BYTES;   // 64 columns x 128 traces = 16 KB
 constexpr int NT_STAGES_MAX = 6;           // ring depth (5 resident / 6 streaming): look-ahead that covers the L2 latency of the W pieces
-constexpr int NT_MAX_KB = 12;
+constexpr int NT_MAX_KB = 24;             // 12 K blocks of the data gradient, twice with split (hi + lo) weights
 constexpr int NUM_THREADS = 192;
 
 struct NtParams {

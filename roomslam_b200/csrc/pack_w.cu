@@ -7,6 +7,10 @@
 //   wt_proj   [6H/128][I/64][8][128][8]   W_ih (scaled) as B pieces of the projection GEMM            (deeper layers)
 //   whhT_img  [2][3H/8][H][8]      W_hh^T: B operand of the BPTT matvec dh = dGh . W_hh
 //   wt_dgrad  [I/128][6H/64][8][128][8]   W_ih^T as B pieces of the data-gradient GEMM dX = dG . W_ih (deeper layers)
+// With split = 1 every weight operand is a PAIR of bf16 images, hi = bf16(w) and lo = bf16(w - hi), stacked along K (the
+// kernels run their K loops over both against the same activations): the weights then enter the tensor core with
+// ~16 mantissa bits.  Rounding the weights to bf16 alone moves the fp32 oracle's gradients by 2.3 % at batch 32 -- a
+// coherent perturbation that does not average out over the batch -- so small batches run with split weights.
 // It replaces ~30 torch cat / stack / permute / cast launches per layer and step.
 #include "common.cuh"
 #include "rec_common.cuh"
@@ -21,10 +25,15 @@ struct PackWParams {
     const float* w_hh[2];
     const float* b_ih[2];
     const float* b_hh[2];
-    int H, I, nck;
+    int H, I, nck, split;                      // split: every weight as a bf16 pair hi + lo (see rs_gru_pack_weights_bf16)
     uint4* whh_img; float* b_hn; float* bias_x; uint4* wt_proj; uint4* whhT_img; uint4* wt_dgrad;
     long long n_a, n_e, n_d, n_f, n_b;         // pieces per region
 };
+
+// part 0: the value itself (rounded to bf16 by the caller's pack8); part 1: what that rounding lost
+__device__ __forceinline__ float hi_lo(float w, int part) {
+    return part == 0 ? w : w - __bfloat162float(__float2bfloat16_rn(w));
+}
 
 __device__ __forceinline__ float bias_x_of(const PackWParams& p, int d, int row) {
     const float s = row < 2 * p.H ? 0.5f : 1.0f;
@@ -43,14 +52,18 @@ __global__ void pack_w_kernel(const PackWParams p) {
             const int c = (e / H3) % p.nck;
             const int d = e / ((long long)H3 * p.nck);
             const float s = row < 2 * H ? 0.5f : 1.0f;
-            if (c < H / 8) {
-                const float4* src = reinterpret_cast<const float4*>(p.w_hh[d] + (long long)row * H + c * 8);
+            const int nh = (H / 8) * (1 + p.split);         // hidden chunks: hi parts, then (split) lo parts
+            if (c < nh) {
+                const int part = c / (H / 8), cc = c % (H / 8);
+                const float4* src = reinterpret_cast<const float4*>(p.w_hh[d] + (long long)row * H + cc * 8);
                 const float4 a = __ldg(src), b = __ldg(src + 1);
-                v[0] = a.x * s; v[1] = a.y * s; v[2] = a.z * s; v[3] = a.w * s; v[4] = b.x * s; v[5] = b.y * s; v[6] = b.z * s; v[7] = b.w * s;
+                const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = hi_lo(w[j] * s, part);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-                if (c == H / 8) {                          // layer-0 input rows
+                if (c == nh) {                             // layer-0 input rows
                     for (int ci = 0; ci < I && ci < 2; ++ci) {
                         const float w = __ldg(p.w_ih[d] + (long long)row * I + ci) * s;
                         const float hi = __bfloat162float(__float2bfloat16_rn(w));
@@ -66,11 +79,13 @@ __global__ void pack_w_kernel(const PackWParams p) {
         }
         e -= p.n_a;
         if (e < p.n_e) {                                   // ---- whhT_img [2][3H/8][H][8]
+            const int nc = (H3 / 8) * (1 + p.split);
             const int u = e % H;
-            const int c = (e / H) % (H3 / 8);
-            const int d = e / ((long long)H * (H3 / 8));
+            const int c = (e / H) % nc;
+            const int d = e / ((long long)H * nc);
+            const int part = c / (H3 / 8), cc = c % (H3 / 8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(p.w_hh[d] + (long long)(c * 8 + j) * H + u);
+            for (int j = 0; j < 8; ++j) v[j] = hi_lo(__ldg(p.w_hh[d] + (long long)(cc * 8 + j) * H + u), part);
             p.whhT_img[e] = pack8(v);
             continue;
         }
@@ -78,14 +93,18 @@ __global__ void pack_w_kernel(const PackWParams p) {
         if (e < p.n_d) {                                   // ---- wt_proj [6H/128][I/64][8][128][8]
             const int r = e & 127;
             const int c8 = (e >> 7) & 7;
-            const int k = (e >> 10) % (I / 64);
-            const int n = (e >> 10) / (I / 64);
+            const int nk = (I / 64) * (1 + p.split);
+            const int kk = (e >> 10) % nk;
+            const int n = (e >> 10) / nk;
+            const int part = kk / (I / 64), k = kk % (I / 64);
             const int grow = n * 128 + r;
             const int d = grow / H3, row = grow % H3;
             const float s = row < 2 * H ? 0.5f : 1.0f;
             const float4* src = reinterpret_cast<const float4*>(p.w_ih[d] + (long long)row * I + k * 64 + c8 * 8);
             const float4 a = __ldg(src), b = __ldg(src + 1);
-            v[0] = a.x * s; v[1] = a.y * s; v[2] = a.z * s; v[3] = a.w * s; v[4] = b.x * s; v[5] = b.y * s; v[6] = b.z * s; v[7] = b.w * s;
+            const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = hi_lo(w[j] * s, part);
             p.wt_proj[e] = pack8(v);
             continue;
         }
@@ -93,13 +112,15 @@ __global__ void pack_w_kernel(const PackWParams p) {
         if (e < p.n_f) {                                   // ---- wt_dgrad [I/128][6H/64][8][128][8]
             const int r = e & 127;
             const int c8 = (e >> 7) & 7;
-            const int k = (e >> 10) % (2 * H3 / 64);
-            const int n = (e >> 10) / (2 * H3 / 64);
+            const int nk = (2 * H3 / 64) * (1 + p.split);
+            const int kk = (e >> 10) % nk;
+            const int n = (e >> 10) / nk;
+            const int part = kk / (2 * H3 / 64), k = kk % (2 * H3 / 64);
             const int col = n * 128 + r;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int grow = k * 64 + c8 * 8 + j;
-                v[j] = __ldg(p.w_ih[grow / H3] + (long long)(grow % H3) * I + col);
+                v[j] = hi_lo(__ldg(p.w_ih[grow / H3] + (long long)(grow % H3) * I + col), part);
             }
             p.wt_dgrad[e] = pack8(v);
             continue;
@@ -117,7 +138,7 @@ __global__ void pack_w_kernel(const PackWParams p) {
 
 }  // namespace
 
-extern "C" int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, void* whh_img, float* b_hn, float* bias_x,
+extern "C" int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, int split, void* whh_img, float* b_hn, float* bias_x,
                                         void* wt_proj, void* whhT_img, void* wt_dgrad, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
@@ -131,13 +152,14 @@ extern "C" int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, voi
         p.w_ih[d] = w[4 * d]; p.w_hh[d] = w[4 * d + 1]; p.b_ih[d] = w[4 * d + 2]; p.b_hh[d] = w[4 * d + 3];
         RS_REQUIRE(p.w_ih[d] && p.w_hh[d] && p.b_ih[d] && p.b_hh[d], "rs_gru_pack_weights_bf16: null weight pointer");
     }
-    p.H = H; p.I = I; p.nck = H / 8 + (layer0 ? 2 : 0);
+    split = split ? 1 : 0;
+    p.H = H; p.I = I; p.split = split; p.nck = (H / 8) * (1 + split) + (layer0 ? 2 : 0);
     p.whh_img = static_cast<uint4*>(whh_img); p.b_hn = b_hn; p.bias_x = bias_x;
     p.wt_proj = static_cast<uint4*>(wt_proj); p.whhT_img = static_cast<uint4*>(whhT_img); p.wt_dgrad = static_cast<uint4*>(wt_dgrad);
     p.n_a = 2LL * p.nck * 3 * H;
-    p.n_e = 2LL * (3 * H / 8) * H;
-    p.n_d = layer0 ? 0 : 6LL * H * I / 8;
-    p.n_f = wt_dgrad ? 6LL * H * I / 8 : 0;
+    p.n_e = 2LL * (3 * H / 8) * H * (1 + split);
+    p.n_d = layer0 ? 0 : 6LL * H * I / 8 * (1 + split);
+    p.n_f = wt_dgrad ? 6LL * H * I / 8 * (1 + split) : 0;
     p.n_b = 2LL * H + 2LL * 3 * H;
     const long long total = p.n_a + p.n_e + p.n_d + p.n_f + p.n_b;
     int blocks = (int)((total + 255) / 256);

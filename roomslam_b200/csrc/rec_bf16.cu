@@ -494,7 +494,8 @@ int pf_dist_env(const char* name, int dflt) {
 
 extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh,
                                const float* b_hn, void* out, void* gates, float* h_n, const int* lengths,
-                               const void* drop_bits, const float* drop_scale, void* out_drop, int B, int T, void* stream_) {
+                               const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T,
+                               void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -508,8 +509,8 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
     }
     RS_REQUIRE((drop_bits != nullptr) == (out_drop != nullptr) && (!drop_bits || drop_scale),
                "rs_rec_fwd_bf16: drop_bits, drop_scale and out_drop go together");
-    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr))
-        return rs::rec_fwd_pair(x, I, P, Whh, b_hn, out, gates, h_n, lengths, drop_bits, drop_scale, out_drop, B, T, nt,
+    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split))
+        return rs::rec_fwd_pair(x, I, P, Whh, b_hn, out, gates, h_n, lengths, drop_bits, drop_scale, out_drop, split, B, T, nt,
                                 pf_dist_env("RS_PF_DIST_FWD", 1), stream);
     FwdParams p = {};
     p.x = x; p.I = I;
@@ -532,15 +533,15 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
 }
 
 extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT,
-                               void* dG, const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T,
-                               void* stream_) {
+                               void* dG, const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B,
+                               int T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(gates && out && WhhT && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
     RS_REQUIRE(!drop_bits || drop_scale, "rs_rec_bwd_bf16: drop_bits needs drop_scale");
-    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr))
-        return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, dG, lengths, drop_bits, drop_scale, B, T, nt, stream);
+    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split))
+        return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, dG, lengths, drop_bits, drop_scale, split, B, T, nt, stream);
     BwdParams p = {};
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);

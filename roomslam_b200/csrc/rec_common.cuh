@@ -68,12 +68,13 @@ __device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
 
 #ifdef __CUDACC__
 // rec_pair.cu: the CTA-pair kernels behind rs_rec_fwd_bf16 / rs_rec_bwd_bf16 (same operands and results as rec_bf16.cu)
-int rec_pair_nt(int B, bool need_drop);     // tiles in flight per pair (1 or 2), or 0 = use the one-CTA-per-tile kernels
+int rec_pair_nt(int B, bool need_pair);     // tiles in flight per pair (1 or 2), or 0 = use the one-CTA-per-tile kernels
 int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int B, int T, int nt,
+                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T, int nt,
                  int pf_dist, cudaStream_t stream);
 int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T, int nt, cudaStream_t stream);
+                 const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T, int nt,
+                 cudaStream_t stream);
 #endif
 
 }  // namespace rs

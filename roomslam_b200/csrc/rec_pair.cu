@@ -35,7 +35,15 @@ constexpr int A_FWD_BYTES = 18 * CHUNK_S;       // 18 KB per tile in flight
 constexpr int H32_BYTES = (H / 4) * CHUNK_S;    // 32 KB per tile in flight (fp32 master copy of h)
 constexpr int W_BWD_BYTES = 48 * CHUNK_S;       // 48 KB: W_hh^T rows of this CTA's 64 hidden units, K = 384 gate rows
 constexpr int A_BWD_BYTES = 48 * CHUNK_S;       // 48 KB per tile in flight (dGh)
-constexpr int EPI_WARPS = 8;                    // per tile in flight: 4 TMEM lane quadrants x 2 groups of 32 hidden units
+// Epilogue warps: always 16 per CTA.  NT = 2: 8 per tile in flight (4 TMEM lane quadrants x 2 groups of 32 hidden units);
+// NT = 1: all 16 on the one tile (4 groups of 16 hidden units): the serial chain per step halves once more.
+template <int NT> struct EpiShape {
+    static constexpr int WG = (NT == 1) ? 4 : 2;        // warp groups per lane quadrant and tile
+    static constexpr int SLOT_WARPS = 4 * WG;           // epilogue warps per tile in flight
+    static constexpr int UPT = 64 / WG;                 // hidden units per thread
+    static constexpr int NGRP = UPT / 8;                // 16-byte chunks (8 units) per thread and step
+};
+constexpr int NUM_THREADS = 64 + 512;
 
 struct FwdPairParams {
     const float* x; int I;
@@ -51,13 +59,16 @@ struct FwdPairParams {
     uint8_t* out_drop;                      // tile-major like out: out (.) mask, the next layer's input (with drop_bits)
     int B, T, n_tiles;
     int pf_dist;
+    int split;                              // 1: Whh holds hi chunks then lo chunks (bf16 pairs per weight), K loop runs over both
 };
 
 template <int NT, bool kVarLen, bool kFusedX>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) rec_fwd_pair_kernel(const FwdPairParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_fwd_pair_kernel(const FwdPairParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;                                   // [18 chunks][192 rows][16 B]
-    uint8_t* a_s = w_s + W_FWD_BYTES;                      // [NT][18 chunks][64 rows][16 B]  h_{t-1} | input columns
+    const int n_hid = 16 * (1 + p.split);                  // hidden-state chunks of W: hi parts, then (split) lo parts
+    const int n_chunks = n_hid + (kFusedX ? 2 : 0);
+    uint8_t* a_s = w_s + n_chunks * W_CHUNK;               // [NT][18 chunks][64 rows][16 B]  h_{t-1} | input columns
     uint8_t* h32_s = a_s + NT * A_FWD_BYTES;               // [NT][32 chunks of 4 floats][64 rows][16 B]
     float* bhn_s = reinterpret_cast<float*>(h32_s + NT * H32_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bhn_s + H);
@@ -66,6 +77,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
     uint64_t* acc_full = bars + 1 + NT;         // [NT], one per CTA (multicast commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NT);
 
+    using ES = EpiShape<NT>;
+    constexpr int EPI_WARPS = ES::SLOT_WARPS, UPT = ES::UPT, NGRP = ES::NGRP;
     const uint32_t rank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -73,7 +86,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
     const int n_slots = min(NT, p.n_tiles - tile0);
     const int T = p.T;
     constexpr bool fused_x = kFusedX;
-    constexpr int n_chunks = fused_x ? 18 : 16;
 
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
@@ -134,18 +146,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
                     if (lane == 0) {
                         const uint32_t a_addr = smem_u32(a_s + s * A_FWD_BYTES);
                         const uint32_t d = tmem_base + s * 256;
+                        for (int part = 0; part <= p.split; ++part) {     // split weights: h . W_hi^T + h . W_lo^T, same A tile
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
-                            const uint64_t db0 = umma_desc_noswz(w_addr + k * 2 * W_CHUNK, W_CHUNK, 128);
-                            const uint64_t db1 = umma_desc_noswz(w_addr + k * 2 * W_CHUNK + 128 * 16, W_CHUNK, 128);
-                            tc_mma_bf16_pair(d, da, db0, idesc256, k != 0);           // r | z  -> columns [0, 128) of each lane half
-                            tc_mma_bf16_pair(d + 128, da, db1, idesc128, k != 0);     // W_hn h -> columns [128, 192)
+                            for (int k = 0; k < 8; ++k) {
+                                const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                                const uint32_t wk = w_addr + (part * 16 + k * 2) * W_CHUNK;
+                                const uint64_t db0 = umma_desc_noswz(wk, W_CHUNK, 128);
+                                const uint64_t db1 = umma_desc_noswz(wk + 128 * 16, W_CHUNK, 128);
+                                tc_mma_bf16_pair(d, da, db0, idesc256, (k | part) != 0);           // r | z  -> columns [0, 128) of each lane half
+                                tc_mma_bf16_pair(d + 128, da, db1, idesc128, (k | part) != 0);     // W_hn h -> columns [128, 192)
+                            }
                         }
                         if (fused_x) {      // layer 0: W_ih x + b as one more K = 16 step of hi / lo split operands
                             const uint64_t da = umma_desc_noswz(a_addr + 16 * CHUNK_S, CHUNK_S, 128);
-                            const uint64_t db0 = umma_desc_noswz(w_addr + 16 * W_CHUNK, W_CHUNK, 128);
-                            const uint64_t db1 = umma_desc_noswz(w_addr + 16 * W_CHUNK + 128 * 16, W_CHUNK, 128);
+                            const uint64_t db0 = umma_desc_noswz(w_addr + n_hid * W_CHUNK, W_CHUNK, 128);
+                            const uint64_t db1 = umma_desc_noswz(w_addr + n_hid * W_CHUNK + 128 * 16, W_CHUNK, 128);
                             tc_mma_bf16_pair(d, da, db0, idesc256, 1u);
                             tc_mma_bf16_pair(d + 192, da, db1, idesc128, 0u);         // W_in x + b_in -> columns [192, 256)
                         }
@@ -170,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
     } else if ((warp - 2) / EPI_WARPS < n_slots) {
         // ===================== epilogue: gates, blend, stores =====================
         const int s = (warp - 2) / EPI_WARPS;
-        const int wg = ((warp - 2) % EPI_WARPS) >> 2;      // which 32 of this lane half's 64 hidden units
+        const int wg = ((warp - 2) % EPI_WARPS) >> 2;      // which UPT of this lane half's 64 hidden units
         const int q = warp & 3;                            // TMEM lane quadrant of this warp
         const int uh = q >> 1;                             // lane half = hidden-unit half
         const int rl = (q & 1) * 32 + lane;                // row within this CTA
@@ -178,8 +193,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
         const int tile = tile0 + s;
         const long long b = (long long)tile * 128 + row;
         const bool live = b < p.B;
-        const int ub = uh * 64 + wg * 32;                  // first hidden unit of this thread
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 256 + wg * 32;
+        const int ub = uh * 64 + wg * UPT;                 // first hidden unit of this thread
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 256 + wg * UPT;
         uint8_t* a_row = a_s + s * A_FWD_BYTES + rl * 16;
         uint8_t* h32_row = h32_s + s * H32_BYTES + rl * 16;
         const uint32_t hr_remote = mapa_cluster(smem_u32(&h_ready[s]), 0);
@@ -195,7 +210,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
             const long long o_off = blk * p.out_block_bytes + (long long)(dir * 16 + ub / 8) * CHUNK_G + row * 16;
             uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
             uint32_t dbits = 0;
-            if (p.drop_bits) dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + ub / 8));
+            if (p.drop_bits)        // the mask bytes of this thread's units sit in one aligned 32-bit word
+                dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + ((ub / 8) & ~3)))
+                        >> (((ub / 8) & 3) * 8);
             uint4 xnext = make_uint4(0, 0, 0, 0);
             const bool write_x = fused_x && ub == 0 && step + 1 < T;
             if (write_x) xnext = pack_x(live ? xrow + (long long)(dir ? t - 1 : t + 1) * p.I : nullptr, p.I);
@@ -208,7 +225,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
             mbar_wait(&acc_full[s], step & 1);
             tc_fence_after();
 #pragma unroll
-            for (int grp = 0; grp < 4; ++grp) {
+            for (int grp = 0; grp < NGRP; ++grp) {
                 const int u0 = ub + grp * 8;
                 uint32_t ar[8], az[8], an[8], ax[8];
                 tmem_ld_32x32b_x8(taddr + grp * 8, ar);
@@ -218,7 +235,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
                 uint4 pc[3];
                 if (!kFusedX) {
                     pc[0] = pv[0]; pc[1] = pv[1]; pc[2] = pv[2];
-                    if (grp < 3) load_p(grp + 1);
+                    if (grp < NGRP - 1) load_p(grp + 1);
                 }
                 tmem_ld_wait();
                 uint32_t wo[4], wd[4], wr[4], wz[4], wn[4], wh[4];      // packed outputs: h, h (.) mask, r, z, n, hn
@@ -293,19 +310,23 @@ struct BwdPairParams {
     const uint8_t* drop_bits;                            // mask of THIS layer's output (applied to d_out) or NULL
     const float* drop_scale;
     int B, T, n_tiles;
+    int split;                                           // 1: WhhT holds 48 hi chunks then 48 lo chunks
 };
 
 template <int NT, bool kVarLen>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) rec_bwd_pair_kernel(const BwdPairParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_bwd_pair_kernel(const BwdPairParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;                                   // [48 chunks][64 rows = hidden units of this CTA][16 B]
-    uint8_t* a_s = w_s + W_BWD_BYTES;                      // [NT][48 chunks][64 rows][16 B]  dGh_t
+    const int w_chunks = 48 * (1 + p.split);
+    uint8_t* a_s = w_s + w_chunks * CHUNK_S;               // [NT][48 chunks][64 rows][16 B]  dGh_t
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + NT * A_BWD_BYTES);
     uint64_t* w_full = bars;
     uint64_t* a_ready = bars + 1;               // [NT] in the even CTA
     uint64_t* acc_full = bars + 1 + NT;         // [NT]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NT);
 
+    using ES = EpiShape<NT>;
+    constexpr int EPI_WARPS = ES::SLOT_WARPS, UPT = ES::UPT, NGRP = ES::NGRP;
     const uint32_t rank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -324,9 +345,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
     if (warp == 0) {
         tmem_alloc_pair<64 * NT>(tmem_slot);
         if (lane == 0) {
-            mbar_expect_tx(w_full, W_BWD_BYTES);
-            const uint8_t* src = p.WhhT + (long long)dir * (48 * CHUNK_G) + rank * 1024;
-            for (int c = 0; c < 48; ++c) bulk_load(w_s + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, w_full);
+            mbar_expect_tx(w_full, w_chunks * CHUNK_S);
+            const uint8_t* src = p.WhhT + (long long)dir * w_chunks * CHUNK_G + rank * 1024;
+            for (int c = 0; c < w_chunks; ++c) bulk_load(w_s + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, w_full);
         }
         mbar_wait(w_full, 0);
     }
@@ -354,11 +375,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a_addr = smem_u32(a_s + s * A_BWD_BYTES);
+                        for (int part = 0; part <= p.split; ++part) {
 #pragma unroll
-                        for (int k = 0; k < 24; ++k) {
-                            const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
-                            const uint64_t db = umma_desc_noswz(w_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
-                            tc_mma_bf16_pair(tmem_base + s * 64, da, db, idesc, 1u);   // accumulates onto the z (.) dh carry in TMEM
+                            for (int k = 0; k < 24; ++k) {
+                                const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                                const uint64_t db = umma_desc_noswz(w_addr + (part * 48 + k * 2) * CHUNK_S, CHUNK_S, 128);
+                                tc_mma_bf16_pair(tmem_base + s * 64, da, db, idesc, 1u);   // accumulates onto the z (.) dh carry in TMEM
+                            }
                         }
                         tc_commit_pair(&acc_full[s]);
                     }
@@ -376,16 +399,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
         const int tile = tile0 + s;
         const long long b = (long long)tile * 128 + row;
         const bool live = b < p.B;
-        const int ub = uh * 64 + wg * 32;
-        const int cb = ub / 8;                             // first of this thread's 4 chunks within the H columns
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 64 + wg * 32;
+        const int ub = uh * 64 + wg * UPT;
+        const int cb = ub / 8;                             // first of this thread's NGRP chunks within the H columns
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 64 + wg * UPT;
         uint8_t* a_row = a_s + s * A_BWD_BYTES + rl * 16;
         const uint32_t ar_remote = mapa_cluster(smem_u32(&a_ready[s]), 0);
         const int len = (kVarLen && live) ? p.lengths[b] : T;
         const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
         // the carry z (.) dh lives in the TMEM accumulator; it starts as d_h_n
 #pragma unroll
-        for (int sc = 0; sc < 4; ++sc) {
+        for (int sc = 0; sc < NGRP; ++sc) {
             uint32_t init[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) init[j] = 0u;
@@ -416,7 +439,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
             raw[5] = p.d_out ? ldg16(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16)
                              : make_uint4(0, 0, 0, 0);
             if (sc == 0 && p.drop_bits)
-                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + cb));
+                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + (cb & ~3)))
+                             >> ((cb & 3) * 8);
         };
         load_raw(0, 0);
         for (int sidx = 0; sidx < T; ++sidx) {             // sidx-th reverse step = forward position T-1-sidx
@@ -431,13 +455,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 * NT, 1) re
                 tc_fence_after();
             }
 #pragma unroll
-            for (int sc = 0; sc < 4; ++sc) {
+            for (int sc = 0; sc < NGRP; ++sc) {
                 uint32_t acc[8];
                 tmem_ld_32x32b_x8(taddr + sc * 8, acc);
                 uint4 cur[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) cur[i] = raw[i];
-                if (sc < 3) load_raw(sidx, sc + 1);
+                if (sc < NGRP - 1) load_raw(sidx, sc + 1);
                 else if (sidx + 1 < T) load_raw(sidx + 1, 0);
                 float r[8], z[8], n[8], hn[8], hp[8], dout[8];
                 unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n); unpack8h(cur[3], hn);
@@ -546,9 +570,9 @@ int rec_mode() {            // RS_REC_MODE: 0 = automatic, 1 = one CTA per tile 
 namespace rs {
 
 // Tiles in flight per CTA pair, or 0 for the one-CTA-per-tile kernels of rec_bf16.cu.
-int rec_pair_nt(int B, bool need_drop) {
+int rec_pair_nt(int B, bool need_pair) {
     const int mode = rec_mode();
-    if (mode == 1 && !need_drop) return 0;
+    if (mode == 1 && !need_pair) return 0;
     if (mode == 2) return 1;
     if (mode == 3) return 2;
     const int n_tiles = (B + 127) / 128;
@@ -556,7 +580,7 @@ int rec_pair_nt(int B, bool need_drop) {
 }
 
 int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int B, int T, int nt,
+                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T, int nt,
                  int pf_dist, cudaStream_t stream) {
     FwdPairParams p = {};
     p.x = x; p.I = I;
@@ -565,14 +589,14 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const fl
     p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
     p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.lengths = lengths;
     p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale; p.out_drop = static_cast<uint8_t*>(out_drop);
-    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.pf_dist = pf_dist;
+    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.pf_dist = pf_dist; p.split = split ? 1 : 0;
     const int pairs = (p.n_tiles + nt - 1) / nt;
-    const int smem = W_FWD_BYTES + nt * (A_FWD_BYTES + H32_BYTES) + H * 4 + 128;
+    const int smem = (16 * (1 + p.split) + (x ? 2 : 0)) * W_CHUNK + nt * (A_FWD_BYTES + H32_BYTES) + H * 4 + 128;
     const dim3 grid(2 * pairs, 2);
 #define RS_LAUNCH_FWD(NT_, VL_, FX_)                                                                                    \
     do {                                                                                                                \
         RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_pair_kernel<NT_, VL_, FX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        rec_fwd_pair_kernel<NT_, VL_, FX_><<<grid, 64 + 256 * NT_, smem, stream>>>(p);                                  \
+        rec_fwd_pair_kernel<NT_, VL_, FX_><<<grid, NUM_THREADS, smem, stream>>>(p);                                  \
     } while (0)
 #define RS_LAUNCH_FWD_X(NT_, VL_)                                                                                       \
     do {                                                                                                                \
@@ -588,7 +612,8 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const fl
 }
 
 int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T, int nt, cudaStream_t stream) {
+                 const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T, int nt,
+                 cudaStream_t stream) {
     BwdPairParams p = {};
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);
@@ -597,14 +622,14 @@ int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const
     p.dG = static_cast<uint8_t*>(dG); p.dg_block_bytes = 8LL * H * 256;
     p.lengths = lengths;
     p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale;
-    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128;
+    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.split = split ? 1 : 0;
     const int pairs = (p.n_tiles + nt - 1) / nt;
-    const int smem = W_BWD_BYTES + nt * A_BWD_BYTES + 128;
+    const int smem = (1 + p.split) * W_BWD_BYTES + nt * A_BWD_BYTES + 128;
     const dim3 grid(2 * pairs, 2);
 #define RS_LAUNCH_BWD(NT_, VL_)                                                                                         \
     do {                                                                                                                \
         RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<NT_, VL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        rec_bwd_pair_kernel<NT_, VL_><<<grid, 64 + 256 * NT_, smem, stream>>>(p);                                       \
+        rec_bwd_pair_kernel<NT_, VL_><<<grid, NUM_THREADS, smem, stream>>>(p);                                       \
     } while (0)
     if (nt == 1) { if (lengths) RS_LAUNCH_BWD(1, true); else RS_LAUNCH_BWD(1, false); }
     else { if (lengths) RS_LAUNCH_BWD(2, true); else RS_LAUNCH_BWD(2, false); }

@@ -317,7 +317,7 @@ class GRULayerFn(torch.autograd.Function):
                 dW_ih[3 * H:], dW_hh[1], db_ih[3 * H:], db_hh[3 * H:])
 
 
-def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None):
+def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None, split_weights=False):
     """Stack of bidirectional layers -> (out (B,T,2H) of the top layer, h_n (2L,B,H)), torch.nn.GRU semantics
     (with `lengths`: those of a packed sequence)."""
     layer_fn = layer_fn or GRULayerFn
@@ -329,14 +329,14 @@ def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None):
     # the fp32 layers multiply their input by the float mask.  `mask` is either a float tensor (L-1, B, T, 2H) or, for the
     # bf16 path, a list of (bits, scale) pairs per layer boundary.
     bits_mode = isinstance(mask, (list, tuple))
-    if mask is not None and not bits_mode and layer_fn is not GRULayerFn:
+    if layer_fn is not GRULayerFn and not bits_mode:
         from .functional_bf16 import drop_bits_from_mask
-        mask = [drop_bits_from_mask(mask[l]) for l in range(num_layers - 1)]
+        mask = [drop_bits_from_mask(mask[l]) for l in range(num_layers - 1)] if mask is not None else [None] * num_layers
         bits_mode = True
     for l in range(num_layers):
         if bits_mode:
             drop = mask[l] if l < num_layers - 1 else None
-            cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths, drop), None, *weights[8 * l: 8 * l + 8])
+            cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths, drop, split_weights), None, *weights[8 * l: 8 * l + 8])
             padded_in = True
             h_all.append(h_n)
             continue

@@ -118,6 +118,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
         padded_in, B, T = meta[:3]
         lengths = meta[3] if len(meta) > 3 else None
         drop = meta[4] if len(meta) > 4 else None
+        split = 1 if (len(meta) > 5 and meta[5]) else 0      # weights as bf16 pairs hi + lo (small batches; csrc/pack_w.cu)
         if mask is not None:
             raise _lib.RoomSlamError("GRULayerBF16Fn: pass dropout as packed bits on the producing layer (meta[4]), not as a float mask")
         if w_hh.shape[1] != H:
@@ -132,18 +133,18 @@ class GRULayerBF16Fn(torch.autograd.Function):
             ws = [t.detach().float().contiguous() for t in (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
             bf = torch.bfloat16
             need_dx = padded_in and ctx.needs_input_grad[0]
-            whh_img = torch.empty(2, H // 8 + (0 if padded_in else 2), 3 * H, 8, device=dev, dtype=bf)
+            whh_img = torch.empty(2, (H // 8) * (1 + split) + (0 if padded_in else 2), 3 * H, 8, device=dev, dtype=bf)
             b_hn = torch.empty(2, H, device=dev)
             bias_x = torch.empty(2, 3 * H, device=dev)
-            wt = torch.empty(6 * H // 128, Il // 64, 8, L.TILE, 8, device=dev, dtype=bf) if padded_in else None
-            whhT_img = torch.empty(2, 3 * H // 8, H, 8, device=dev, dtype=bf)
-            wt_dgrad = torch.empty(Il // 128, 6 * H // 64, 8, L.TILE, 8, device=dev, dtype=bf) if need_dx else None
+            wt = torch.empty(6 * H // 128, (Il // 64) * (1 + split), 8, L.TILE, 8, device=dev, dtype=bf) if padded_in else None
+            whhT_img = torch.empty(2, (3 * H // 8) * (1 + split), H, 8, device=dev, dtype=bf)
+            wt_dgrad = torch.empty(Il // 128, (6 * H // 64) * (1 + split), 8, L.TILE, 8, device=dev, dtype=bf) if need_dx else None
             if not padded_in and Il > 2:
                 raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 2")
             if padded_in and Il != 2 * H:
                 raise _lib.RoomSlamError("bf16 mode: deeper layers take the 2H-column output of the layer below")
             wp = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in ws])
-            _lib.call("rs_gru_pack_weights_bf16", ctypes.addressof(wp), H, Il, _p(whh_img), _p(b_hn), _p(bias_x), _p(wt), _p(whhT_img),
+            _lib.call("rs_gru_pack_weights_bf16", ctypes.addressof(wp), H, Il, split, _p(whh_img), _p(b_hn), _p(bias_x), _p(wt), _p(whhT_img),
                       _p(wt_dgrad), st)
             # (the recurrence kernels zero the pad rows t' = 0, T + 1 of what they write)
             out = L.empty_tm(B, T, 2 * H, dev, zero_pads=False)
@@ -157,20 +158,20 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 x = xin.contiguous().float()
                 with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
                     _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
-                              _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
+                              _p(d_bits), _p(d_scale), _p(out_drop), split, B, T, st)
                 saved_in = x
             else:
                 X = xin
                 P = torch.empty(tiles, T + 2, 6 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
                 with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
-                    _nt(X, Il, [8 * k for k in range(Il // 64)], wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
+                    _nt(X, Il, [8 * k for k in range(Il // 64)] * (1 + split), wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
                 with ktime("rec_fwd_bf16_kernel", rec_flops):
                     _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
-                              _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
+                              _p(d_bits), _p(d_scale), _p(out_drop), split, B, T, st)
                 del P
                 saved_in = X
-        ctx.meta = (padded_in, B, T, Il)
+        ctx.meta = (padded_in, B, T, Il, split)
         ctx.drop = drop
         ctx.lengths = lengths
         # save_for_backward (not ctx attributes): `out` is an OUTPUT of this node; holding it in a plain attribute
@@ -183,7 +184,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
     @staticmethod
     @_lib.on_tensor_device
     def backward(ctx, d_out, d_h_n):
-        padded_in, B, T, Il = ctx.meta
+        padded_in, B, T, Il, split = ctx.meta
         out, gates, saved_in, whhT_img, wt_dgrad = ctx.saved_tensors
         if gates is None:
             raise RuntimeError("GRULayerBF16Fn: forward ran without saving activations (nothing required grad)")
@@ -197,7 +198,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
             with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
                 d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
                 _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths),
-                          _p(d_bits), _p(d_scale), B, T, st)
+                          _p(d_bits), _p(d_scale), split, B, T, st)
             # ALL weight / bias gradients of the layer in one fused pass over dG (12 roles, see csrc/gemm_blk.cu):
             #   ih roles (dir, g in r,z,n): dG block ^T . X            -> dW_ih rows, bias sums of r, z, n
             #   hh roles (dir, g in r,z,hn): dG block ^T . h(t' -/+ 1) -> dW_hh rows, bias sum of hn
@@ -243,7 +244,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                     wt = wt_dgrad                                                  # [Il/128][12][8][128][8]
                     kch = [d * 64 + g * 16 + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in (0, 1)]
                     with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
-                        _nt(dG, 8 * H, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
+                        _nt(dG, 8 * H, kch * (1 + split), wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
                     d_xin = dX
         return (d_xin, None, None, dW_ih[:3 * H], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * H:], dW_hh[1], db_ih[1], db_hh[1])
 

@@ -81,7 +81,8 @@ class Decoder(nn.Module):
 
 class RoomSLAM(nn.Module):
     def __init__(self, input_size: int = 2, hidden_size: int = 128, num_layers: int = 2, max_objects: int = 10,
-                 num_classes: int = 4, dropout: float = 0.1, decoder_hidden: int = 256, precision: str = "fp32"):
+                 num_classes: int = 4, dropout: float = 0.1, decoder_hidden: int = 256, precision: str = "fp32",
+                 bf16_split_weights: Optional[bool] = None):
         super().__init__()
         if precision not in ("fp32", "bf16", "auto"):
             raise ValueError(f"precision must be 'fp32', 'bf16' or 'auto', got {precision!r}")
@@ -90,6 +91,11 @@ class RoomSLAM(nn.Module):
         self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
         self.max_objects, self.num_classes, self.dropout = max_objects, num_classes, dropout
         self.precision = precision
+        # bf16 mode: feed every GRU weight to the tensor core as a bf16 PAIR hi + lo (~16 mantissa bits) instead of one bf16.
+        # Rounding the weights is a coherent perturbation (it does not average out over the batch like activation rounding):
+        # alone it moves the gradients by 2.3 % at batch 32.  None = automatic: split below SPLIT_WEIGHTS_BELOW traces per
+        # step, where the recurrence is latency-bound and the doubled MMA work is free; plain bf16 weights above.
+        self.bf16_split_weights = bf16_split_weights
         self.encoder = GRUParams(input_size, hidden_size, num_layers)
         self.decoder = Decoder(2 * hidden_size, decoder_hidden, max_objects, num_classes, precision)
 
@@ -130,6 +136,7 @@ class RoomSLAM(nn.Module):
         return out, h_n
 
     AUTO_BF16_MIN_BATCH = 256
+    SPLIT_WEIGHTS_BELOW = 1024
 
     def _use_bf16(self, batch: int) -> bool:
         """'auto': the tensor-core bf16 kernels from 256 traces per step (where their 2e-2 gradient bar holds)
@@ -156,7 +163,8 @@ class RoomSLAM(nn.Module):
                                 for s in seeds]
             else:
                 dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
-        return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn, lengths)
+        split = bf16 and (self.bf16_split_weights if self.bf16_split_weights is not None else x.shape[0] < self.SPLIT_WEIGHTS_BELOW)
+        return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn, lengths, split_weights=split)
 
     def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
                 lengths: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
