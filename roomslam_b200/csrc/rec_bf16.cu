@@ -509,7 +509,7 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
     }
     RS_REQUIRE((drop_bits != nullptr) == (out_drop != nullptr) && (!drop_bits || drop_scale),
                "rs_rec_fwd_bf16: drop_bits, drop_scale and out_drop go together");
-    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split))
+    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split, false))
         return rs::rec_fwd_pair(x, I, P, Whh, b_hn, out, gates, h_n, lengths, drop_bits, drop_scale, out_drop, split, B, T, nt,
                                 pf_dist_env("RS_PF_DIST_FWD", 1), stream);
     FwdParams p = {};
@@ -540,7 +540,7 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
     if (B == 0 || T == 0) return 0;        // nothing to do: empty tensors carry null pointers
     RS_REQUIRE(gates && out && WhhT && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
     RS_REQUIRE(!drop_bits || drop_scale, "rs_rec_bwd_bf16: drop_bits needs drop_scale");
-    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split))
+    if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split, true))
         return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, dG, lengths, drop_bits, drop_scale, split, B, T, nt, stream);
     BwdParams p = {};
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;

@@ -68,7 +68,7 @@ __device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
 
 #ifdef __CUDACC__
 // rec_pair.cu: the CTA-pair kernels behind rs_rec_fwd_bf16 / rs_rec_bwd_bf16 (same operands and results as rec_bf16.cu)
-int rec_pair_nt(int B, bool need_pair);     // tiles in flight per pair (1 or 2), or 0 = use the one-CTA-per-tile kernels
+int rec_pair_nt(int B, bool need_pair, bool backward);   // tiles in flight per pair (1 or 2); 0 = one-CTA-per-tile kernels
 int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
                  const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T, int nt,
                  int pf_dist, cudaStream_t stream);

@@ -541,9 +541,9 @@ __global__ void pack_drop_mask_kernel(const float* __restrict__ mask, int B, int
 }
 
 // Bernoulli(keep) bits straight from a counter-based generator (no (B, T, C) float mask in HBM): the training default.
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-    return static_cast<uint32_t>(x);
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {       // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+    return x;
 }
 __global__ void gen_drop_bits_kernel(uint8_t* __restrict__ bits, long long n_bytes, unsigned long long seed, uint32_t keep_thr16,
                                      float* __restrict__ scale) {
@@ -551,10 +551,10 @@ __global__ void gen_drop_bits_kernel(uint8_t* __restrict__ bits, long long n_byt
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_bytes / 4; e += (long long)gridDim.x * blockDim.x) {
         uint32_t word = 0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {                     // two 16-bit uniforms per hash
-            const uint32_t h = mix32(seed + (static_cast<uint64_t>(e) << 4) + k);
-            word |= ((h & 0xffffu) < keep_thr16 ? 1u : 0u) << (2 * k);
-            word |= ((h >> 16) < keep_thr16 ? 1u : 0u) << (2 * k + 1);
+        for (int k = 0; k < 8; ++k) {                      // four 16-bit uniforms per 64-bit hash
+            const uint64_t h = mix64(seed + (static_cast<uint64_t>(e) << 3) + k + 0x9e3779b97f4a7c15ULL * (k + 1));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) word |= (((h >> (16 * q)) & 0xffffu) < keep_thr16 ? 1u : 0u) << (4 * k + q);
         }
         reinterpret_cast<uint32_t*>(bits)[e] = word;
     }
@@ -569,14 +569,21 @@ int rec_mode() {            // RS_REC_MODE: 0 = automatic, 1 = one CTA per tile 
 
 namespace rs {
 
-// Tiles in flight per CTA pair, or 0 for the one-CTA-per-tile kernels of rec_bf16.cu.
-int rec_pair_nt(int B, bool need_pair) {
+// Tiles in flight per CTA pair, or 0 for the one-CTA-per-tile kernels of rec_bf16.cu (RS_REC_MODE=1: A/B comparisons only).
+// Measured on B200 (tools/pair_check.sh, ms per 500-step launch pair at B = 1024 / 8192):
+//   forward : one CTA per tile 5.1 / 6.3   pair NT=1 2.7 / 6.3   pair NT=2 4.1 / 5.8
+//   backward: one CTA per tile 5.5 / 7.4   pair NT=1 2.9 / 6.9   pair NT=2 5.8 / 8.0
+// Forward: NT = 1 while every tile can have its own pair of SMs in both directions (<= 37 tiles), else NT = 2 (the MMA of one
+// tile runs under the epilogue of the other).  Backward: always NT = 1 -- the BPTT epilogue is bound by the latency of its
+// gate / h / d_out loads, which two waves of half-size CTAs hide better than two tiles on one register-capped CTA.
+int rec_pair_nt(int B, bool need_pair, bool backward) {
     const int mode = rec_mode();
     if (mode == 1 && !need_pair) return 0;
     if (mode == 2) return 1;
     if (mode == 3) return 2;
+    if (backward) return 1;
     const int n_tiles = (B + 127) / 128;
-    return (n_tiles * 4 <= 148) ? 1 : 2;       // NT = 1 while every tile can have its own pair of SMs in both directions
+    return (n_tiles * 4 <= 148) ? 1 : 2;
 }
 
 int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,

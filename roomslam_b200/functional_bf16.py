@@ -156,7 +156,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
             X = None
             if not padded_in:
                 x = xin.contiguous().float()
-                with ktime("rec_fwd_bf16_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
+                with ktime("rec_fwd_pair_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
                     _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
                               _p(d_bits), _p(d_scale), _p(out_drop), split, B, T, st)
                 saved_in = x
@@ -166,7 +166,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
                     _nt(X, Il, [8 * k for k in range(Il // 64)] * (1 + split), wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
-                with ktime("rec_fwd_bf16_kernel", rec_flops):
+                with ktime("rec_fwd_pair_kernel", rec_flops):
                     _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
                               _p(d_bits), _p(d_scale), _p(out_drop), split, B, T, st)
                 del P
@@ -195,7 +195,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
             d_out = d_out.contiguous().to(torch.bfloat16) if d_out is not None else None
             d_h_n = d_h_n.contiguous().float() if d_h_n is not None else None
             dG = torch.empty(tiles, T + 2, 8 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
-            with ktime("rec_bwd_bf16_kernel", 2.0 * B * T * 2 * 3 * H * H):
+            with ktime("rec_bwd_pair_kernel", 2.0 * B * T * 2 * 3 * H * H):
                 d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
                 _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths),
                           _p(d_bits), _p(d_scale), split, B, T, st)

@@ -124,7 +124,7 @@ def test_precision_auto_picks_kernels_by_batch():
     from roomslam_b200 import RoomSLAM, functional as Fn, synth
     torch.manual_seed(0)
     m = RoomSLAM(dropout=0.0, precision="auto").cuda().train()
-    for B, want in ((32, "gru_fwd_f32_kernel"), (256, "rec_fwd_bf16_kernel")):
+    for B, want in ((32, "gru_fwd_f32_kernel"), (256, "rec_fwd_pair_kernel")):
         x, tgt = synth.make_sample(B, 60, 10, seed=1, device="cuda")
         Fn.enable_kernel_timing(True)
         m.compute_loss(m(x), tgt)["total"].backward()
