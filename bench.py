@@ -57,15 +57,15 @@ def gru_flops_per_trace(T=SEQ_LEN, H=HIDDEN, L=LAYERS, I=2):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle on the box's host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_train_baseline(steps: int, warmup: int, sample_batch: int = 32):
+def cpu_train_baseline(steps: int, warmup: int, sample_batch: int = 32, hidden: int = HIDDEN, seq_len: int = SEQ_LEN):
     from oracle.room_slam_ref import RoomSLAM as Ref
     from roomslam_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = Ref(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=0.0).train()
+    model = Ref(hidden_size=hidden, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=0.0).train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
-    x, tgt = synth.make_sample(sample_batch, SEQ_LEN, MAX_OBJECTS, seed=0)
+    x, tgt = synth.make_sample(sample_batch, seq_len, MAX_OBJECTS, seed=0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -78,7 +78,7 @@ def cpu_train_baseline(steps: int, warmup: int, sample_batch: int = 32):
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return {"value": sample_batch / sec, "unit": "traces/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_batch} traces x {SEQ_LEN} steps per step, fp32 torch {torch.__version__} CPU oracle "
+            "sample": f"{sample_batch} traces x {seq_len} steps per step (H {hidden}), fp32 torch {torch.__version__} CPU oracle "
                       f"(fwd+loss+bwd+clip+AdamW), {steps} timed steps", "ms_per_step": sec * 1e3}
 
 
@@ -224,17 +224,17 @@ def timed(fn, steps, warmup, dist_on):
 class TrainLeg:
     """One training configuration (model + flat buffers + optimizer + one synthetic batch resident on host and device)."""
 
-    def __init__(self, batch, rank, world, precision, dropout=0.0, seed_base=0):
+    def __init__(self, batch, rank, world, precision, dropout=0.0, seed_base=0, hidden=HIDDEN, seq_len=SEQ_LEN):
         from roomslam_b200 import RoomSLAM, synth
         from roomslam_b200.train_utils import FlatParams, GradReducer, FusedAdamW, HostBatchPrefetcher
         torch.manual_seed(0)
         self.world, self.batch = world, batch
-        self.model = RoomSLAM(hidden_size=HIDDEN, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=dropout,
+        self.model = RoomSLAM(hidden_size=hidden, num_layers=LAYERS, max_objects=MAX_OBJECTS, dropout=dropout,
                               precision=precision).cuda().train()
         self.flat = FlatParams(self.model)
         self.reducer = GradReducer(self.flat)
         self.opt = FusedAdamW(self.flat, lr=1e-3, max_grad_norm=1.0)
-        x_host, tgt_host = synth.make_sample(batch, SEQ_LEN, MAX_OBJECTS, seed=seed_base + rank)
+        x_host, tgt_host = synth.make_sample(batch, seq_len, MAX_OBJECTS, seed=seed_base + rank)
         self.x_host = x_host.pin_memory()
         self.tgt_host = {k: v.pin_memory() for k, v in tgt_host.items()}
         self.x_dev = self.x_host.cuda()
@@ -398,6 +398,26 @@ def run_ours(args):
                             "the recurrence kernels)", "value": B / (ms_d / 1e3), "unit": "traces/s", "ms_per_step": ms_d,
                 "slowdown_vs_p0": ms_d / ms_train - 1.0}
 
+    # ---- single-GPU extra: BASELINE config 4 (long-trace variant: H 256, T 4000, batch 1024) on the tensor-core path ----------
+    c4 = None
+    if not dist_on and not args.skip_c4:
+        c4_leg = TrainLeg(1024, 0, 1, "bf16", hidden=256, seq_len=4000)
+        ms_c4 = timed(c4_leg.step_resident, 3, 2, False)
+        F_.enable_kernel_timing(True)
+        c4_leg.step_resident()
+        torch.cuda.synchronize()
+        c4_kernels = F_.collect_kernel_timing()
+        F_.enable_kernel_timing(False)
+        c4_leg.free()
+        del c4_leg
+        c4_flops = gru_flops_per_trace(T=4000, H=256)
+        c4 = {"workload": "BASELINE config 4: bi-GRU H=256 L=2 seq_len=4000, batch 1024, bf16, fwd+loss+bwd+clip+AdamW "
+                          "(W_hh streamed from L2 by the recurrence kernels, csrc/rec_wide.cu)",
+              "value": 1024 / (ms_c4 / 1e3), "unit": "traces/s", "ms_per_step": ms_c4, "steps": 3, "warmup": 2,
+              "algorithmic_gflop_per_trace": c4_flops / 1e9, "flop_bound_ms": c4_flops * 1024 / (pk["tflops_sustained"] * 1e12) * 1e3,
+              "frac_of_flop_bound": c4_flops * 1024 / (pk["tflops_sustained"] * 1e12) * 1e3 / ms_c4,
+              "kernel_ms": {k: v[0] for k, v in c4_kernels.items()}}
+
     # ---- heatmap -------------------------------------------------------------------------------------------
     hm = OccupancyHeatmapBaseline()
     pts = synth.make_traces(n_tr, SEQ_LEN, seed=1000 + rank, device="cuda")
@@ -489,6 +509,10 @@ def run_ours(args):
         if c1 is not None:
             line["c1"] = c1
             line["dropout"] = drop
+        if c4 is not None:
+            line["c4"] = c4
+            cb4 = cpu_train_baseline(1, 0, sample_batch=8, hidden=256, seq_len=4000)
+            line["c4"]["cpu_baseline"] = {k: cb4[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if world == 1:
             cb = cpu_train_baseline(2, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -710,6 +734,7 @@ def main():
                          "weak: they are per GPU.  The other mode is measured too and reported under its name")
     ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="traces (global for strong scaling, per GPU for weak)")
     ap.add_argument("--heatmap-traces", type=int, default=HEATMAP_TRACES, help="traces (global / per GPU, as --batch)")
+    ap.add_argument("--skip-c4", action="store_true", help="skip the BASELINE config 4 leg (H 256, T 4000; ~63 GB of HBM)")
     ap.add_argument("--suite", default="headline", choices=["headline", "next"],
                     help="'next': one JSON line per SURVEY.md 8(f) row instead of the headline line (single GPU)")
     args = ap.parse_args()

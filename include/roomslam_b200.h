@@ -182,6 +182,19 @@ int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
                     const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T,
                     void* stream);
+/* The same two kernels for hidden_size = 256 (BASELINE config 4: H 256, T 4000), where W_hh no longer fits in shared memory:
+ * each CTA of the pair streams its half of the weights from L2 through a ring of bulk copies once per time step
+ * (csrc/rec_wide.cu).  Tile-major operands as above with H = 256 (P 6H, out 2H, dG 8H columns; gates
+ * [tiles][T][2][128][128][8] fp16).  Wst: [2 dirs][2 ranks][9 (layer 0) or 8 stages][2 K steps][2 chunks][384 rows][8]
+ * bf16, rows = r | z | n gate rows of hidden units [128 rank, 128 rank + 128) (r, z scaled by 1/2), K step k = hidden
+ * units [16 k, 16 k + 16); layer 0: K step 16 = the input chunk (w_hi, w_hi, w_lo per input column, b_hi, b_lo) and a zero
+ * chunk, K step 17 = 0.  WTst: [2][2][8 stages][6 K steps][2 chunks][128 rows][8] bf16 = W_hh^T with rows = hidden units
+ * [128 rank, +128) and K = the 768 gate rows in r | z | n order. */
+int rs_rec_fwd_bf16_wide(const float* x, int I, const void* P, const void* Wst, const float* b_hn, void* out, void* gates,
+                         float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop,
+                         int B, int T, void* stream);
+int rs_rec_bwd_bf16_wide(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WTst, void* dG,
+                         const int* lengths, const void* drop_bits, const float* drop_scale, int B, int T, void* stream);
 /* Inter-layer dropout (README.md:114; analogue src/benchmark/model.py:13,20) without a (B, T, 2H) multiply in HBM: the
  * mask travels as ONE BIT per element, [tiles][T][128 rows][C/8 bytes] (C = 2H), plus a device scalar scale = 1/keep.
  * rs_rec_fwd_bf16 with drop_bits writes out_drop = out (.) mask * scale next to out (the next layer's input);

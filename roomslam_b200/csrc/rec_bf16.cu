@@ -541,7 +541,11 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
     RS_REQUIRE(gates && out && WhhT && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
     RS_REQUIRE(!drop_bits || drop_scale, "rs_rec_bwd_bf16: drop_bits needs drop_scale");
     if (const int nt = rs::rec_pair_nt(B, drop_bits != nullptr || split, true))
-        return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, dG, lengths, drop_bits, drop_scale, split, B, T, nt, stream);
+        // L2 prefetch (RS_PF_DIST_BWD steps ahead) is off by default: at 8192 traces the kernel runs against the HBM roof and
+        // prefetched lines are evicted before use (round 1), at 1024 traces the step is bound by its compute / sync chain, not
+        // by load latency (7.28 ms per training step without, 7.35 ms with distance 2)
+        return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, dG, lengths, drop_bits, drop_scale, split, B, T, nt,
+                                pf_dist_env("RS_PF_DIST_BWD", 0), stream);
     BwdParams p = {};
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);

@@ -74,7 +74,7 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const fl
                  int pf_dist, cudaStream_t stream);
 int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
                  const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T, int nt,
-                 cudaStream_t stream);
+                 int pf_dist, cudaStream_t stream);
 #endif
 
 }  // namespace rs

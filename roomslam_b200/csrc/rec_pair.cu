@@ -311,6 +311,7 @@ struct BwdPairParams {
     const float* drop_scale;
     int B, T, n_tiles;
     int split;                                           // 1: WhhT holds 48 hi chunks then 48 lo chunks
+    int pf_dist;                                         // L2 prefetch distance in steps (0 = off)
 };
 
 template <int NT, bool kVarLen>
@@ -387,6 +388,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     }
                     __syncwarp();
                 }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== L2 prefetcher (latency mode): saved gates, h_{t-1}, d_out of a later reverse step ==========
+        if (lane == 0 && p.pf_dist > 0) {
+            for (int sidx = 0; sidx < T; ++sidx) {
+                const int s2 = sidx + p.pf_dist;
+                if (s2 < T) {
+                    const int t = dir ? s2 : (T - 1 - s2);
+                    const int t_prev = dir ? t + 1 : t - 1;
+                    for (int s = 0; s < n_slots; ++s) {
+                        const long long blk = (long long)(tile0 + s) * (T + 2) + t + 1, blk_prev = (long long)(tile0 + s) * (T + 2) + t_prev + 1;
+                        l2_prefetch(p.gates + (((long long)(tile0 + s) * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(rank * 32) * CHUNK_G, 32 * CHUNK_G);
+                        l2_prefetch(p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
+                        if (p.d_out) l2_prefetch(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
+                    }
+                }
+                if (sidx < T - 1) mbar_wait(&acc_full[0], sidx & 1);   // the MMA of reverse step sidx retired: the epilogue moved on
             }
         }
     } else if (warp >= 2 && (warp - 2) / EPI_WARPS < n_slots) {
@@ -620,8 +639,9 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const fl
 
 int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
                  const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T, int nt,
-                 cudaStream_t stream) {
+                 int pf_dist, cudaStream_t stream) {
     BwdPairParams p = {};
+    p.pf_dist = pf_dist;
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);
     p.out = static_cast<const uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;

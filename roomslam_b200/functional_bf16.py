@@ -249,6 +249,164 @@ class GRULayerBF16Fn(torch.autograd.Function):
         return (d_xin, None, None, dW_ih[:3 * H], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * H:], dW_hh[1], db_ih[1], db_hh[1])
 
 
+class GRULayerBF16WideFn(torch.autograd.Function):
+    """GRULayerBF16Fn for hidden_size = 256 (BASELINE config 4).  Same tile-major operands and the same GEMM kernels; the
+    recurrence runs on csrc/rec_wide.cu, which streams W_hh from L2 (it no longer fits in shared memory).  The GEMM calls are
+    cut to the kernels' limits (<= 1024 output columns per projection launch, <= 18 weight-gradient roles of <= 256 columns
+    per launch).  The weight images are laid out with torch ops here: a step of this configuration takes ~100 ms."""
+
+    HW = 256
+
+    @staticmethod
+    @_lib.on_tensor_device
+    def forward(ctx, xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        ctx.set_materialize_grads(False)
+        _need_cuda(xin, w_ih, w_hh)
+        HW = GRULayerBF16WideFn.HW
+        padded_in, B, T = meta[:3]
+        lengths = meta[3] if len(meta) > 3 else None
+        drop = meta[4] if len(meta) > 4 else None
+        if mask is not None:
+            raise _lib.RoomSlamError("GRULayerBF16WideFn: pass dropout as packed bits on the producing layer (meta[4])")
+        if w_hh.shape[1] != HW:
+            raise _lib.RoomSlamError(f"GRULayerBF16WideFn is built for hidden_size = {HW}")
+        dev, st, bf = xin.device, _stream(xin), torch.bfloat16
+        need_grad = any(ctx.needs_input_grad)
+        tiles, Il = L.n_tiles(B), w_ih.shape[1]
+        with torch.no_grad():
+            half = torch.ones(3 * HW, device=dev)
+            half[:2 * HW] = 0.5
+            w_hh_cat = torch.stack([w_hh, w_hh_r], 0).float()                      # [2, 3H, H]
+            w_ih_cat = torch.cat([w_ih, w_ih_r], 0).float()                        # [6H, Il]
+            b_hn = torch.stack([b_hh[2 * HW:], b_hh_r[2 * HW:]], 0).float().contiguous()
+            bias_x = torch.stack([b_ih, b_ih_r], 0).float().clone()
+            bias_x[0, :2 * HW] += b_hh[:2 * HW]
+            bias_x[1, :2 * HW] += b_hh_r[:2 * HW]
+            bias_x *= half[None, :]
+            whs = w_hh_cat * half[None, :, None]
+            w_ih_fwd = (w_ih_cat.view(2, 3 * HW, Il) * half[None, :, None])
+            rows = lambda t, r: torch.cat([t[:, g * HW + 128 * r: g * HW + 128 * r + 128] for g in range(3)], 1)   # noqa: E731
+            per_rank = []
+            for r in (0, 1):
+                img = rows(whs, r).view(2, 384, HW // 16, 2, 8).permute(0, 2, 3, 1, 4)          # [2][16 K steps][2 chunks][384][8]
+                if not padded_in:
+                    if Il > 2:
+                        raise _lib.RoomSlamError("bf16 mode fuses the layer-0 projection for input_size <= 2")
+                    w_hi = w_ih_fwd.to(bf).float()
+                    b_hi = bias_x.to(bf).float()
+                    xcols = torch.zeros(2, 3 * HW, 16, device=dev)
+                    for c in range(Il):
+                        xcols[:, :, 3 * c] = w_hi[:, :, c]
+                        xcols[:, :, 3 * c + 1] = w_hi[:, :, c]
+                        xcols[:, :, 3 * c + 2] = w_ih_fwd[:, :, c] - w_hi[:, :, c]
+                    xcols[:, :, 6] = b_hi
+                    xcols[:, :, 7] = bias_x - b_hi
+                    xstep = rows(xcols, r).view(2, 384, 1, 2, 8).permute(0, 2, 3, 1, 4)         # the input K step
+                    img = torch.cat([img, xstep, torch.zeros_like(xstep)], 1)                   # + a zero K step: 9 full stages
+                per_rank.append(img)
+            wst = torch.stack(per_rank, 1).to(bf).contiguous()                     # [2 dirs][2 ranks][K steps][2][384][8]
+            out = L.empty_tm(B, T, 2 * HW, dev, zero_pads=False)
+            out_drop = L.empty_tm(B, T, 2 * HW, dev, zero_pads=False) if drop is not None else None
+            d_bits, d_scale = drop if drop is not None else (None, None)
+            h_n = torch.empty(2, B, HW, device=dev)
+            gates = torch.empty(tiles, T, 2, 4 * HW // 8, L.TILE, 8, device=dev, dtype=bf) if need_grad else None
+            rec_flops = 2.0 * B * T * 2 * 3 * HW * HW
+            if not padded_in:
+                x = xin.contiguous().float()
+                with ktime("rec_fwd_wide_kernel", rec_flops + 2.0 * B * T * 6 * HW * Il):
+                    _lib.call("rs_rec_fwd_bf16_wide", _p(x), Il, 0, _p(wst), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
+                              _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
+                saved_in = x
+            else:
+                if Il != 2 * HW:
+                    raise _lib.RoomSlamError("bf16 mode: deeper layers take the 2H-column output of the layer below")
+                P = torch.empty(tiles, T + 2, 6 * HW // 8, L.TILE, 8, device=dev, dtype=bf)
+                wt = L.tile_weight_nt(w_ih_fwd.reshape(6 * HW, Il))                # [12][Il/64][8][128][8]
+                bias_flat = bias_x.reshape(-1).contiguous()
+                with ktime("blk_gemm_nt_kernel(projection)", 2.0 * tiles * L.TILE * (T + 2) * 6 * HW * Il):
+                    for part in (0, 1):                                            # 1536 output columns: two launches of 768
+                        _nt(xin, Il, [8 * k for k in range(Il // 64)], wt[6 * part: 6 * part + 6].contiguous(), 6, P, 6 * HW,
+                            96 * part, bias_flat[768 * part: 768 * part + 768].contiguous(), tiles * (T + 2), st)
+                with ktime("rec_fwd_wide_kernel", rec_flops):
+                    _lib.call("rs_rec_fwd_bf16_wide", 0, 0, _p(P), _p(wst), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
+                              _p(d_bits), _p(d_scale), _p(out_drop), B, T, st)
+                del P
+                saved_in = xin
+        ctx.meta = (padded_in, B, T, Il)
+        ctx.drop, ctx.lengths = drop, lengths
+        ctx.save_for_backward(out, gates, saved_in, w_ih_cat, w_hh_cat)
+        return (out_drop if out_drop is not None else out), h_n
+
+    @staticmethod
+    @_lib.on_tensor_device
+    def backward(ctx, d_out, d_h_n):
+        HW = GRULayerBF16WideFn.HW
+        padded_in, B, T, Il = ctx.meta
+        out, gates, saved_in, w_ih_cat, w_hh_cat = ctx.saved_tensors
+        if gates is None:
+            raise RuntimeError("GRULayerBF16WideFn: forward ran without saving activations (nothing required grad)")
+        dev, bf = out.device, torch.bfloat16
+        st = torch.cuda.current_stream(dev).cuda_stream
+        tiles, HC = L.n_tiles(B), HW // 8
+        with torch.no_grad():
+            d_out = d_out.contiguous().to(bf) if d_out is not None else None
+            d_h_n = d_h_n.contiguous().float() if d_h_n is not None else None
+            whhT = w_hh_cat.transpose(1, 2)                                        # [2, H, 3H]
+            wtst = torch.stack([whhT[:, 128 * r: 128 * r + 128].reshape(2, 128, 3 * HW // 16, 2, 8).permute(0, 2, 3, 1, 4)
+                                for r in (0, 1)], 1).to(bf).contiguous()           # [2][2][48 K steps][2][128][8]
+            dG = torch.empty(tiles, T + 2, 8 * HC, L.TILE, 8, device=dev, dtype=bf)
+            d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
+            with ktime("rec_bwd_wide_kernel", 2.0 * B * T * 2 * 3 * HW * HW):
+                _lib.call("rs_rec_bwd_bf16_wide", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(wtst), _p(dG), _p(ctx.lengths),
+                          _p(d_bits), _p(d_scale), B, T, st)
+            dW_hh = torch.zeros(2, 3 * HW, HW, device=dev)
+            sums = torch.zeros(2, 4, HW, device=dev)             # per direction: r | z | n | hn column sums of dG
+            ones = _ones_block(dev)
+            if not padded_in:
+                xa_tm = torch.empty(tiles, T + 2, 2, L.TILE, 8, device=dev, dtype=bf)
+                _lib.call("rs_pack_x_tm", _p(saved_in), B, T, Il, _p(xa_tm), st)
+                dW_ih_buf = torch.zeros(6 * HW, 16, device=dev)
+            else:
+                dW_ih_buf = torch.zeros(6 * HW, Il, device=dev)
+            flops = 2.0 * tiles * L.TILE * T * (6 * HW * (Il if padded_in else 16) + 6 * HW * HW + 8 * HW * 16)
+            with ktime("blk_wgrad_kernel", flops):
+                for d in (0, 1):                                 # one launch per direction: <= 18 roles of one 128-row gate block
+                    sh = -1 if d == 0 else 1
+                    roles = []
+                    for mb in (0, 1):                            # the two 128-row halves of a 256-row gate block
+                        m0 = mb * 128
+                        if not padded_in:
+                            for g in (0, 1):
+                                roles.append((d * 4 * HC + g * HC + mb * 16, out, 2 * HW, d * HC, HW, sh, dW_hh[d, g * HW + m0:], HW,
+                                              sums[d, g, m0:], xa_tm, dW_ih_buf[(d * 3 + g) * HW + m0:]))
+                            roles.append((d * 4 * HC + 3 * HC + mb * 16, out, 2 * HW, d * HC, HW, sh, dW_hh[d, 2 * HW + m0:], HW,
+                                          sums[d, 3, m0:], None, None))
+                            roles.append((d * 4 * HC + 2 * HC + mb * 16, None, 0, 0, 0, 0, None, 0, sums[d, 2, m0:], xa_tm,
+                                          dW_ih_buf[(d * 3 + 2) * HW + m0:]))
+                        else:
+                            for g in (0, 1, 2):                  # r, z, n against the layer input, 256 columns at a time
+                                for nb in range(Il // 256):
+                                    roles.append((d * 4 * HC + g * HC + mb * 16, saved_in, Il, nb * 32, 256, 0,
+                                                  dW_ih_buf[(d * 3 + g) * HW + m0:, nb * 256:], Il, sums[d, g, m0:] if nb == 0 else None,
+                                                  None, None))
+                            for gi, g in enumerate((0, 1, 3)):   # r, z, hn against the shifted hidden state
+                                roles.append((d * 4 * HC + g * HC + mb * 16, out, 2 * HW, d * HC, HW, sh, dW_hh[d, gi * HW + m0:], HW,
+                                              sums[d, 3, m0:] if g == 3 else None, None, None))
+                    _wgrad(dG, 8 * HW, ones, roles, tiles, T, st)
+            db_ih = sums[:, :3].reshape(2, 3 * HW)
+            db_hh = torch.cat([sums[:, :2].reshape(2, 2 * HW), sums[:, 3]], 1)
+            dW_ih = dW_ih_buf[:, :Il].contiguous() if not padded_in else dW_ih_buf
+            d_xin = None
+            if padded_in and ctx.needs_input_grad[0]:
+                dX = torch.empty(tiles, T + 2, Il // 8, L.TILE, 8, device=dev, dtype=bf)
+                wt = L.tile_weight_nt(w_ih_cat.t().contiguous())                   # [Il/128][6H/64][8][128][8]
+                kch = [d * 4 * HC + g * HC + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in range(HW // 64)]
+                with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * HW * Il):
+                    _nt(dG, 8 * HW, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
+                d_xin = dX
+        return (d_xin, None, None, dW_ih[:3 * HW], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * HW:], dW_hh[1], db_ih[1], db_hh[1])
+
+
 def _gemm_nt(A, Bw, C, bias, flags=0):
     """C[M,N] = act(A[M,K] . Bw[N,K]^T + bias): TMA-fed tcgen05 GEMM (csrc/gemm_tc.cu)."""
     M, K = A.shape

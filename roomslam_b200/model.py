@@ -142,13 +142,13 @@ class RoomSLAM(nn.Module):
         """'auto': the tensor-core bf16 kernels from 256 traces per step (where their 2e-2 gradient bar holds)
         when the shape fits them (H = 128, at most 2 input columns); the fp32 kernels (1e-4) otherwise."""
         if self.precision == "auto":
-            return batch >= self.AUTO_BF16_MIN_BATCH and self.hidden_size == 128 and self.input_size <= 2
+            return batch >= self.AUTO_BF16_MIN_BATCH and self.hidden_size in (128, 256) and self.input_size <= 2
         return self.precision == "bf16"
 
     def _encode(self, x, dropout_mask, lengths=None):
         bf16 = self._use_bf16(x.shape[0])
         self.decoder.precision = "bf16" if bf16 else "fp32"
-        layer_fn = _bf16_layer_fn() if bf16 else F_.GRULayerFn
+        layer_fn = _bf16_layer_fn(self.hidden_size) if bf16 else F_.GRULayerFn
         # inter-layer dropout (README.md:114): an explicit float mask (decision D4) is used as given; without one, training
         # mode draws it -- as packed bits on the device for the bf16 kernels, as a float mask for the fp32 kernels
         if dropout_mask is not None:
@@ -163,7 +163,7 @@ class RoomSLAM(nn.Module):
                                 for s in seeds]
             else:
                 dropout_mask = self.make_dropout_mask(x.shape[0], x.shape[1], device=x.device)
-        split = bf16 and (self.bf16_split_weights if self.bf16_split_weights is not None else x.shape[0] < self.SPLIT_WEIGHTS_BELOW)
+        split = bf16 and self.hidden_size == 128 and (self.bf16_split_weights if self.bf16_split_weights is not None else x.shape[0] < self.SPLIT_WEIGHTS_BELOW)
         return F_.gru_encoder(x, dropout_mask, self.num_layers, self.encoder.flat_weights(), layer_fn, lengths, split_weights=split)
 
     def forward(self, x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
@@ -200,9 +200,12 @@ class RoomSLAM(nn.Module):
         return {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
 
 
-def _bf16_layer_fn():
-    try:
-        from .functional_bf16 import GRULayerBF16Fn
-    except ImportError as e:  # pragma: no cover
-        raise _lib.RoomSlamError(f"bf16 tensor-core path unavailable: {e}")
-    return GRULayerBF16Fn
+def _bf16_layer_fn(hidden_size: int):
+    """The tensor-core recurrence exists for hidden_size 128 (W_hh resident in shared memory, csrc/rec_pair.cu) and 256
+    (W_hh streamed from L2, csrc/rec_wide.cu); other sizes run the fp32 kernels."""
+    from .functional_bf16 import GRULayerBF16Fn, GRULayerBF16WideFn
+    if hidden_size == 128:
+        return GRULayerBF16Fn
+    if hidden_size == 256:
+        return GRULayerBF16WideFn
+    raise _lib.RoomSlamError(f"bf16 mode is built for hidden_size 128 or 256 (got {hidden_size}); use precision='fp32'")

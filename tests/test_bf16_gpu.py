@@ -62,6 +62,58 @@ def test_bf16_rejects_other_hidden_sizes():
         dev(torch.zeros(2, 4, 2, device="cuda"))
 
 
+@pytest.mark.parametrize("B,T,L,use_mask", [(130, 40, 2, False), (200, 64, 2, True), (3, 5, 1, False), (129, 7, 2, False)])
+def test_hidden_256_matches_oracle(B, T, L, use_mask):
+    """hidden_size = 256 (README.md:153: HIDDEN_SIZE is a hyper-parameter; BASELINE config 4) on the tensor-core path
+    that streams W_hh from L2 (csrc/rec_wide.cu), against the fp32 CPU oracle: 2e-2."""
+    torch.manual_seed(B + T)
+    ref = RefRoomSLAM(hidden_size=256, num_layers=L, dropout=0.1 if use_mask else 0.0)
+    dev = RoomSLAM(hidden_size=256, num_layers=L, dropout=ref.dropout, precision="bf16").cuda()
+    dev.load_state_dict(ref.state_dict())
+    ref.train(use_mask); dev.train(use_mask)
+    x, tgt = synth.make_sample(B, T, 10, seed=B)
+    mask = ref.make_dropout_mask(B, T, torch.Generator().manual_seed(1)) if use_mask else None
+    enc_ref, hn_ref = ref.encode(x, mask)
+    loss_ref = ref.compute_loss(ref(x, mask), tgt)
+    loss_ref["total"].backward()
+    xm = mask.cuda() if mask is not None else None
+    enc_dev, hn_dev = dev.encode(x.cuda(), xm)
+    loss_dev = dev.compute_loss(dev(x.cuda(), xm), to_cuda(tgt))
+    loss_dev["total"].backward()
+    assert rel_err(enc_dev, enc_ref) < RTOL and rel_err(hn_dev, hn_ref) < RTOL
+    for k in LOSS_KEYS:
+        assert abs(loss_dev[k].item() - loss_ref[k].item()) <= RTOL * max(abs(loss_ref[k].item()), 1e-6), k
+    ref_grads = dict(ref.named_parameters())
+    tol = RTOL if B >= 100 else 5e-2          # a handful of traces: bf16 rounding noise does not average out (see module doc)
+    errs = {pn: l2_err(p.grad, ref_grads[pn].grad) for pn, p in dev.named_parameters() if pn.startswith("encoder.")}
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+
+
+def test_c4_shape_hidden_256_seq_4000():
+    """BASELINE config 4's shape at a batch the CPU oracle can follow (64 traces x 4000 steps, H = 256): hidden states,
+    losses and encoder gradients of the bf16 tensor-core path against the fp32 oracle within 2e-2; lengths vary so the
+    packed-sequence path of the wide kernels is exercised at the full 4000 steps too (second half of the batch)."""
+    torch.manual_seed(4)
+    ref = RefRoomSLAM(hidden_size=256, dropout=0.0).train()
+    dev = RoomSLAM(hidden_size=256, dropout=0.0, precision="bf16").cuda().train()
+    dev.load_state_dict(ref.state_dict())
+    x, tgt = synth.make_sample(64, 4000, 10, seed=2)
+    _, hn_ref = ref.encode(x)
+    loss_ref = ref.compute_loss(ref(x), tgt)
+    loss_ref["total"].backward()
+    _, hn_dev = dev.encode(x.cuda())
+    loss_dev = dev.compute_loss(dev(x.cuda()), to_cuda(tgt))
+    loss_dev["total"].backward()
+    assert rel_err(hn_dev, hn_ref) < RTOL
+    for k in LOSS_KEYS:
+        assert abs(loss_dev[k].item() - loss_ref[k].item()) <= RTOL * max(abs(loss_ref[k].item()), 1e-6), k
+    ref_grads = dict(ref.named_parameters())
+    errs = {pn: l2_err(p.grad, ref_grads[pn].grad) for pn, p in dev.named_parameters() if pn.startswith("encoder.")}
+    bad = {k: v for k, v in errs.items() if not v < RTOL}
+    assert not bad, bad
+
+
 def _grad_errs(dev, ref_grads):
     return {k: l2_err(p.grad, ref_grads[k]) for k, p in dev.named_parameters()}
 
