@@ -171,17 +171,19 @@ int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, int split, voi
  * Whh is then [2][18][384][8] bf16 with chunk 16 = per gate row (w_hi, w_hi, w_lo) per input and (b_hi, b_lo), chunk
  * 17 = 0.  Deeper layers: P tile-major (6H columns, bias folded in) and Whh [2][16][384][8].  The r and z rows of all
  * weights / biases carry the factor 1/2 of sigma(a) = tanh(a/2)/2 + 1/2.  b_hn [2][H], out tile-major (2H columns,
- * zero pad rows), gates [tiles][T][2][64][128][8] fp16 (NULL for inference), h_n [2][B][H] fp32. */
+ * zero pad rows), gates [tiles][T][2][48][128][8] fp16 = r | z | n (NULL for inference; W_hn h + b_hn is NOT saved, the
+ * backward kernel recomputes it), h_n [2][B][H] fp32. */
 int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
                     void* gates, float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale,
                     void* out_drop, int split, int B, int T, void* stream);
 /* x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (zero padded): layer-0 input for rs_blk_wgrad. */
 int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream);
 /* Backward through time.  d_out tile-major (2H) or NULL, d_h_n [2][B][H] or NULL, WhhT [2][48][128][8] bf16,
- * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks). */
-int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                    const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T,
-                    void* stream);
+ * dG tile-major (8H columns: per direction r | z | n | hn gate-gradient blocks).  Whh (the forward image, whh_chunks chunks
+ * per direction) and b_hn: the kernel recomputes W_hn h_{t-1} + b_hn on the tensor core from the bulk-copied h_{t-1} tile. */
+int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT,
+                    const void* Whh, int whh_chunks, const float* b_hn, void* dG, const int* lengths, const void* drop_bits,
+                    const float* drop_scale, int split, int B, int T, void* stream);
 /* The same two kernels for hidden_size = 256 (BASELINE config 4: H 256, T 4000), where W_hh no longer fits in shared memory:
  * each CTA of the pair streams its half of the weights from L2 through a ring of bulk copies once per time step
  * (csrc/rec_wide.cu).  Tile-major operands as above with H = 256 (P 6H, out 2H, dG 8H columns; gates

@@ -1,5 +1,5 @@
-// Device helpers shared by the bf16 recurrence kernels (rec_bf16.cu: one CTA per 128-trace tile; rec_pair.cu: a CTA pair
-// per tile on tcgen05 cta_group::2): fast tanh, bf16 / fp16 pack and unpack of 16-byte pieces, the layer-0 input columns.
+// Device helpers shared by the bf16 recurrence kernels (rec_pair.cu: H = 128, rec_wide.cu: H = 256; a CTA pair per tile on
+// tcgen05 cta_group::2): fast tanh, bf16 / fp16 pack and unpack of 16-byte pieces, the layer-0 input columns.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -68,13 +68,13 @@ __device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
 
 #ifdef __CUDACC__
 // rec_pair.cu: the CTA-pair kernels behind rs_rec_fwd_bf16 / rs_rec_bwd_bf16 (same operands and results as rec_bf16.cu)
-int rec_pair_nt(int B, bool need_pair, bool backward);   // tiles in flight per pair (1 or 2); 0 = one-CTA-per-tile kernels
+int rec_fwd_nt(int B);                      // tiles in flight per pair of the forward kernel (1 or 2)
 int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
                  const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T, int nt,
                  int pf_dist, cudaStream_t stream);
-int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T, int nt,
-                 int pf_dist, cudaStream_t stream);
+int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, const void* Whh,
+                 int whh_chunks, const float* b_hn, void* dG, const int* lengths, const void* drop_bits, const float* drop_scale,
+                 int split, int B, int T, int pf_dist, cudaStream_t stream);
 #endif
 
 }  // namespace rs

@@ -208,7 +208,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             const long long blk = (long long)tile * (T + 2) + t + 1;
             const uint8_t* pblk = kFusedX ? nullptr : p.P + blk * p.p_block_bytes + (long long)(dir * 48 + ub / 8) * CHUNK_G + row * 16;
             const long long o_off = blk * p.out_block_bytes + (long long)(dir * 16 + ub / 8) * CHUNK_G + row * 16;
-            uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
+            uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (48LL * CHUNK_G) + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
             uint32_t dbits = 0;
             if (p.drop_bits)        // the mask bytes of this thread's units sit in one aligned 32-bit word
                 dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + ((ub / 8) & ~3)))
@@ -238,10 +238,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     if (grp < NGRP - 1) load_p(grp + 1);
                 }
                 tmem_ld_wait();
-                uint32_t wo[4], wd[4], wr[4], wz[4], wn[4], wh[4];      // packed outputs: h, h (.) mask, r, z, n, hn
+                uint32_t wo[4], wd[4], wr[4], wz[4], wn[4];             // packed outputs: h, h (.) mask, r, z, n
 #pragma unroll
                 for (int jp = 0; jp < 4; ++jp) {                        // two hidden units at a time keeps the live set small
-                    float hv2[2], rv2[2], zv2[2], nv2[2], hnv2[2], od2[2];
+                    float hv2[2], rv2[2], zv2[2], nv2[2], od2[2];
                     const float2 ho2 = *reinterpret_cast<const float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8);
                     const float2 bh2 = *reinterpret_cast<const float2*>(bhn_s + u0 + 2 * jp);
                     float2 pr2 = make_float2(0.f, 0.f), pz2 = pr2, pn2 = pr2;
@@ -263,14 +263,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                         const float hn = __uint_as_float(an[j]) + (e ? bh2.y : bh2.x);
                         const float n = tanh_fast(fmaf(r, hn, e ? pn2.y : pn2.x));
                         const float h = active ? fmaf(z, ho - n, n) : ho;
-                        hv2[e] = h; rv2[e] = r; zv2[e] = z; nv2[e] = n; hnv2[e] = hn;
+                        hv2[e] = h; rv2[e] = r; zv2[e] = z; nv2[e] = n;
                         od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
                     }
                     *reinterpret_cast<float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8) = make_float2(hv2[0], hv2[1]);
                     wo[jp] = f2_to_bf2(hv2[0], hv2[1]);
                     wd[jp] = f2_to_bf2(od2[0], od2[1]);
                     wr[jp] = f2_to_h2(rv2[0], rv2[1]); wz[jp] = f2_to_h2(zv2[0], zv2[1]);
-                    wn[jp] = f2_to_h2(nv2[0], nv2[1]); wh[jp] = f2_to_h2(hnv2[0], hnv2[1]);
+                    wn[jp] = f2_to_h2(nv2[0], nv2[1]);
                     if (step == T - 1 && live)
                         *reinterpret_cast<float2*>(p.h_n + ((long long)dir * p.B + b) * H + u0 + 2 * jp) = make_float2(hv2[0], hv2[1]);
                 }
@@ -282,8 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     stg16(gblk + (long long)(0 * 16 + grp) * CHUNK_G, make_uint4(wr[0], wr[1], wr[2], wr[3]));
                     stg16(gblk + (long long)(1 * 16 + grp) * CHUNK_G, make_uint4(wz[0], wz[1], wz[2], wz[3]));
                     stg16(gblk + (long long)(2 * 16 + grp) * CHUNK_G, make_uint4(wn[0], wn[1], wn[2], wn[3]));
-                    stg16(gblk + (long long)(3 * 16 + grp) * CHUNK_G, make_uint4(wh[0], wh[1], wh[2], wh[3]));
-                }
+                }   // W_hn h + b_hn is not saved: the backward kernel recomputes it on the tensor core
             }
             if (write_x) *reinterpret_cast<uint4*>(a_row + 16 * CHUNK_S) = xnext;
             fence_proxy_async();        // h_t written with ordinary stores -> visible to the tensor core of this SM
@@ -299,59 +298,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Backward through time: one 128-trace tile per CTA pair (16 epilogue warps per CTA, 16 hidden units per thread).
+//   dh_{t-1} = z (.) dh_t + dGh_t . W_hh   one MMA chain (K = 384) accumulating onto the carry that lives in TMEM.
+// W_hn h_{t-1} + b_hn is NOT saved by the forward pass (it would be a fourth 16-bit gate block: 2.1 GB written and 2.1 GB
+// read per layer at the benchmark shape): with W_hh halved per CTA there is room for the h_{t-1} tile and the W_hn rows, so
+// the kernel recomputes it on the tensor core -- warp 1 bulk-copies the h_{t-1} block of the tile two steps ahead (two
+// stages; it is the `out` block the epilogue used to read with per-thread loads), the even CTA's warp 1 issues
+// hn = h_{t-1} . W_hn^T (N = 128, K = 128) into one of two 64-column TMEM buffers as soon as both CTAs' tiles landed, and
+// the epilogue reads hn from TMEM and h_{t-1} from shared memory.  Same bf16 operands and K order as the forward MMA: the
+// recomputed value is the forward's fp32 accumulator, not its fp16 rounding.
 struct BwdPairParams {
     const uint8_t* d_out; long long dout_block_bytes;
     const float* d_h_n;
-    const uint8_t* gates;
+    const uint8_t* gates;                                // [tiles][T][2][48 chunks: r | z | n][128][8] fp16
     const uint8_t* out; long long out_block_bytes;
-    const uint8_t* WhhT;                                 // [2][48][128][8] bf16
+    const uint8_t* WhhT;                                 // [2][48 (x2 split)][128][8] bf16
+    const uint8_t* Whh;                                  // forward image [2][16 (x2 split) (+2)][384][8]: its n rows are W_hn
+    int whh_chunks;                                      // chunks per direction of the forward image
+    const float* b_hn;                                   // [2][H]
     uint8_t* dG; long long dg_block_bytes;
     const int* lengths;
     const uint8_t* drop_bits;                            // mask of THIS layer's output (applied to d_out) or NULL
     const float* drop_scale;
     int B, T, n_tiles;
-    int split;                                           // 1: WhhT holds 48 hi chunks then 48 lo chunks
-    int pf_dist;                                         // L2 prefetch distance in steps (0 = off)
+    int split;                                           // 1: weight images hold hi chunks then lo chunks
+    int pf_dist;                                         // L2 prefetch distance of the gate / d_out blocks in steps (0 = off)
 };
 
-template <int NT, bool kVarLen>
+constexpr int HP_BYTES = 16 * CHUNK_S;                   // 16 KB: the h_{t-1} tile of this CTA's 64 rows (K-major A operand)
+
+template <bool kVarLen>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_bwd_pair_kernel(const BwdPairParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* w_s = smem;                                   // [48 chunks][64 rows = hidden units of this CTA][16 B]
-    const int w_chunks = 48 * (1 + p.split);
-    uint8_t* a_s = w_s + w_chunks * CHUNK_S;               // [NT][48 chunks][64 rows][16 B]  dGh_t
-    uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + NT * A_BWD_BYTES);
+    const int w_chunks = 48 * (1 + p.split), n_hid = 16 * (1 + p.split);
+    uint8_t* w_s = smem;                                   // [48 chunks][64 rows = hidden units of this CTA][16 B]   W_hh^T
+    uint8_t* a_s = w_s + w_chunks * CHUNK_S;               // [48 chunks][64 rows][16 B]  dGh_t
+    uint8_t* wn_s = a_s + A_BWD_BYTES;                     // [16 chunks][64 rows = hidden units of this CTA][16 B]   W_hn
+    uint8_t* hp_s = wn_s + n_hid * CHUNK_S;                // [2 stages][16 chunks][64 rows][16 B]  h_{t-1}
+    float* bhn_s = reinterpret_cast<float*>(hp_s + 2 * HP_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bhn_s + H);
     uint64_t* w_full = bars;
-    uint64_t* a_ready = bars + 1;               // [NT] in the even CTA
-    uint64_t* acc_full = bars + 1 + NT;         // [NT]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NT);
+    uint64_t* a_ready = bars + 1;               // even CTA: dGh_t of both CTAs written (32 warps)
+    uint64_t* acc_full = bars + 2;              // both: the dh MMA chain retired (multicast commit)
+    uint64_t* hp_full = bars + 3;               // [2] this CTA's h_{t-1} tile landed (bulk-copy bytes)
+    uint64_t* hp_rdy = bars + 5;                // [2] even CTA: both CTAs' tiles landed (2 arrivals)
+    uint64_t* hn_full = bars + 7;               // [2] both: the hn MMA retired (multicast commit)
+    uint64_t* hp_free = bars + 9;               // [2] this CTA's 16 epilogue warps are done with the stage (tile and TMEM buffer)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
-    using ES = EpiShape<NT>;
-    constexpr int EPI_WARPS = ES::SLOT_WARPS, UPT = ES::UPT, NGRP = ES::NGRP;
+    constexpr int UPT = 16, NGRP = 2;
     const uint32_t rank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
-    const int tile0 = (blockIdx.x >> 1) * NT;
-    const int n_slots = min(NT, p.n_tiles - tile0);
+    const int tile = blockIdx.x >> 1;
     const int T = p.T;
 
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
-        for (int s = 0; s < NT; ++s) {
-            mbar_init(&a_ready[s], 2 * EPI_WARPS);
-            mbar_init(&acc_full[s], 1);
-        }
+        mbar_init(a_ready, 2 * 16);
+        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&hp_full[i], 1); mbar_init(&hp_rdy[i], 2); mbar_init(&hn_full[i], 1); mbar_init(&hp_free[i], 16); }
         fence_mbar_init();
     }
     if (warp == 0) {
-        tmem_alloc_pair<64 * NT>(tmem_slot);
+        tmem_alloc_pair<256>(tmem_slot);        // dh accumulator [0, 64), hn buffers [64, 128) and [128, 192)
         if (lane == 0) {
-            mbar_expect_tx(w_full, w_chunks * CHUNK_S);
+            mbar_expect_tx(w_full, (w_chunks + n_hid) * CHUNK_S);
             const uint8_t* src = p.WhhT + (long long)dir * w_chunks * CHUNK_G + rank * 1024;
             for (int c = 0; c < w_chunks; ++c) bulk_load(w_s + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, w_full);
+            const uint8_t* srcn = p.Whh + (long long)dir * p.whh_chunks * (384 * 16) + (256 + rank * 64) * 16;
+            for (int c = 0; c < n_hid; ++c) bulk_load(wn_s + c * CHUNK_S, srcn + (long long)c * (384 * 16), 1024, w_full);
         }
         mbar_wait(w_full, 0);
     }
+    for (int i = threadIdx.x; i < H; i += blockDim.x) bhn_s[i] = p.b_hn[dir * H + i];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -359,70 +379,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
     const uint32_t tmem_base = *tmem_slot;
 
     // pad rows of dG (the weight / data gradient GEMMs run over all T + 2 rows of a tile)
-    for (int i = threadIdx.x; i < n_slots * 2 * 64 * ROWS; i += blockDim.x) {
-        const int rl = i % ROWS, c = (i / ROWS) % 64, pad = (i / (ROWS * 64)) % 2, s = i / (ROWS * 128);
-        const long long off = ((long long)(tile0 + s) * (T + 2) + (pad ? T + 1 : 0)) * p.dg_block_bytes
+    for (int i = threadIdx.x; i < 2 * 64 * ROWS; i += blockDim.x) {
+        const int rl = i % ROWS, c = (i / ROWS) % 64, pad = i / (ROWS * 64);
+        const long long off = ((long long)tile * (T + 2) + (pad ? T + 1 : 0)) * p.dg_block_bytes
                               + (long long)(dir * 64 + c) * CHUNK_G + (rank * ROWS + rl) * 16;
         stg16(p.dG + off, make_uint4(0, 0, 0, 0));
     }
 
     if (warp == 0) {
         if (rank == 0) {
+            // ===================== dh matvec issuer =====================
             constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
-            const uint32_t w_addr = smem_u32(w_s);
+            const uint32_t w_addr = smem_u32(w_s), a_addr = smem_u32(a_s);
             for (int sidx = 0; sidx < T - 1; ++sidx) {     // the result of the last reverse step is unused
-                for (int s = 0; s < n_slots; ++s) {
-                    mbar_wait_cluster(&a_ready[s], sidx & 1);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_addr = smem_u32(a_s + s * A_BWD_BYTES);
-                        for (int part = 0; part <= p.split; ++part) {
+                mbar_wait_cluster(a_ready, sidx & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    for (int part = 0; part <= p.split; ++part) {
 #pragma unroll
-                            for (int k = 0; k < 24; ++k) {
-                                const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
-                                const uint64_t db = umma_desc_noswz(w_addr + (part * 48 + k * 2) * CHUNK_S, CHUNK_S, 128);
-                                tc_mma_bf16_pair(tmem_base + s * 64, da, db, idesc, 1u);   // accumulates onto the z (.) dh carry in TMEM
-                            }
+                        for (int k = 0; k < 24; ++k) {
+                            const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            const uint64_t db = umma_desc_noswz(w_addr + (part * 48 + k * 2) * CHUNK_S, CHUNK_S, 128);
+                            tc_mma_bf16_pair(tmem_base, da, db, idesc, 1u);   // accumulates onto the z (.) dh carry in TMEM
                         }
-                        tc_commit_pair(&acc_full[s]);
                     }
-                    __syncwarp();
+                    tc_commit_pair(acc_full);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===================== L2 prefetcher (latency mode): saved gates, h_{t-1}, d_out of a later reverse step ==========
-        if (lane == 0 && p.pf_dist > 0) {
+        // ===================== h_{t-1} tile producer (both CTAs) + hn issuer (even CTA) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+            const uint32_t wn_addr = smem_u32(wn_s);
+            const uint32_t rdy_remote[2] = {mapa_cluster(smem_u32(&hp_rdy[0]), 0), mapa_cluster(smem_u32(&hp_rdy[1]), 0)};
             for (int sidx = 0; sidx < T; ++sidx) {
-                const int s2 = sidx + p.pf_dist;
-                if (s2 < T) {
-                    const int t = dir ? s2 : (T - 1 - s2);
-                    const int t_prev = dir ? t + 1 : t - 1;
-                    for (int s = 0; s < n_slots; ++s) {
-                        const long long blk = (long long)(tile0 + s) * (T + 2) + t + 1, blk_prev = (long long)(tile0 + s) * (T + 2) + t_prev + 1;
-                        l2_prefetch(p.gates + (((long long)(tile0 + s) * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(rank * 32) * CHUNK_G, 32 * CHUNK_G);
-                        l2_prefetch(p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
-                        if (p.d_out) l2_prefetch(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
-                    }
+                const int st = sidx & 1;
+                const uint32_t ph = (sidx >> 1) & 1;
+                const int t = dir ? sidx : (T - 1 - sidx);
+                const int t_prev = dir ? t + 1 : t - 1;
+                if (sidx >= 2) mbar_wait(&hp_free[st], ph ^ 1);        // the epilogue of step sidx - 2 is done with this stage
+                mbar_expect_tx(&hp_full[st], HP_BYTES);
+                const uint8_t* src = p.out + ((long long)tile * (T + 2) + t_prev + 1) * p.out_block_bytes + (long long)(dir * 16) * CHUNK_G + rank * 1024;
+                for (int c = 0; c < 16; ++c) bulk_load(hp_s + st * HP_BYTES + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, &hp_full[st]);
+                if (p.pf_dist > 0 && sidx + p.pf_dist < T) {           // optional L2 prefetch of a later step's gate / d_out blocks
+                    const int t2 = dir ? sidx + p.pf_dist : (T - 1 - sidx - p.pf_dist);
+                    l2_prefetch(p.gates + (((long long)tile * T + t2) * 2 + dir) * (48LL * CHUNK_G) + (long long)(rank * 24) * CHUNK_G, 24 * CHUNK_G);
+                    if (p.d_out) l2_prefetch(p.d_out + ((long long)tile * (T + 2) + t2 + 1) * p.dout_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
                 }
-                if (sidx < T - 1) mbar_wait(&acc_full[0], sidx & 1);   // the MMA of reverse step sidx retired: the epilogue moved on
+                mbar_wait(&hp_full[st], ph);
+                mbar_arrive_cluster(rdy_remote[st]);
+                if (rank == 0) {
+                    mbar_wait(&hp_rdy[st], ph);
+                    tc_fence_after();
+                    const uint32_t hp_addr = smem_u32(hp_s + st * HP_BYTES);
+                    for (int part = 0; part <= p.split; ++part) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t da = umma_desc_noswz(hp_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            const uint64_t db = umma_desc_noswz(wn_addr + (part * 16 + k * 2) * CHUNK_S, CHUNK_S, 128);
+                            tc_mma_bf16_pair(tmem_base + 64 + st * 64, da, db, idesc, (k | part) != 0);
+                        }
+                    }
+                    tc_commit_pair(&hn_full[st]);
+                }
             }
         }
-    } else if (warp >= 2 && (warp - 2) / EPI_WARPS < n_slots) {
-        const int s = (warp - 2) / EPI_WARPS;
-        const int wg = ((warp - 2) % EPI_WARPS) >> 2;
+    } else {
+        // ===================== epilogue =====================
+        const int wg = (warp - 2) >> 2;                    // which 16 of this lane half's 64 hidden units
         const int q = warp & 3;
         const int uh = q >> 1;
         const int rl = (q & 1) * 32 + lane;
         const int row = rank * ROWS + rl;
-        const int tile = tile0 + s;
         const long long b = (long long)tile * 128 + row;
         const bool live = b < p.B;
         const int ub = uh * 64 + wg * UPT;
-        const int cb = ub / 8;                             // first of this thread's NGRP chunks within the H columns
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 64 + wg * UPT;
-        uint8_t* a_row = a_s + s * A_BWD_BYTES + rl * 16;
-        const uint32_t ar_remote = mapa_cluster(smem_u32(&a_ready[s]), 0);
+        const int cb = ub / 8;                             // first of this thread's 2 chunks within the H columns
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + wg * UPT;
+        uint8_t* a_row = a_s + rl * 16;
+        const uint32_t ar_remote = mapa_cluster(smem_u32(a_ready), 0);
         const int len = (kVarLen && live) ? p.lengths[b] : T;
         const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
         // the carry z (.) dh lives in the TMEM accumulator; it starts as d_h_n
@@ -442,49 +479,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         }
         tmem_st_wait();
 
-        // raw 16-byte pieces of one chunk (8 units): r, z, n, hn (fp16), h_prev, d_out (bf16)
-        uint4 raw[6];
+        // raw 16-byte pieces of one chunk (8 units): r, z, n (fp16), d_out (bf16)
+        uint4 raw[4];
         uint32_t dbits_next = 0;
         auto load_raw = [&](int sidx, int sc) {
-            const int fstep = T - 1 - sidx;
-            const int t = dir ? (T - 1 - fstep) : fstep;
-            const int t_prev = dir ? t + 1 : t - 1;
+            const int t = dir ? sidx : (T - 1 - sidx);
             const long long blk = (long long)tile * (T + 2) + t + 1;
-            const long long blk_prev = (long long)tile * (T + 2) + t_prev + 1;
-            const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * (64LL * CHUNK_G) + (long long)(cb + sc) * CHUNK_G + row * 16;
+            const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * (48LL * CHUNK_G) + (long long)(cb + sc) * CHUNK_G + row * 16;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) raw[g] = ldg16(gblk + (long long)(g * 16) * CHUNK_G);
-            raw[4] = ldg16(p.out + blk_prev * p.out_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16);
-            raw[5] = p.d_out ? ldg16(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16)
+            for (int g = 0; g < 3; ++g) raw[g] = ldg16(gblk + (long long)(g * 16) * CHUNK_G);
+            raw[3] = p.d_out ? ldg16(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16)
                              : make_uint4(0, 0, 0, 0);
             if (sc == 0 && p.drop_bits)
                 dbits_next = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + (cb & ~3)))
                              >> ((cb & 3) * 8);
         };
         load_raw(0, 0);
-        for (int sidx = 0; sidx < T; ++sidx) {             // sidx-th reverse step = forward position T-1-sidx
-            const int fstep = T - 1 - sidx;
-            const int t = dir ? (T - 1 - fstep) : fstep;
+        for (int sidx = 0; sidx < T; ++sidx) {             // sidx-th reverse step = forward position T-1-sidx (dir 0)
+            const int t = dir ? sidx : (T - 1 - sidx);
+            const int st = sidx & 1;
             const long long blk = (long long)tile * (T + 2) + t + 1;
             const bool active = !kVarLen || t < len;
             uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 64 + cb) * CHUNK_G + row * 16;
+            const uint8_t* hp_row = hp_s + st * HP_BYTES + rl * 16;
             const uint32_t dbits = dbits_next;
-            if (sidx > 0) {
-                mbar_wait(&acc_full[s], (sidx - 1) & 1);
-                tc_fence_after();
-            }
+            mbar_wait(&hn_full[st], (sidx >> 1) & 1);      // W_hn h_{t-1} of this step is in TMEM, the h_{t-1} tile in shared memory
+            if (sidx > 0) mbar_wait(acc_full, (sidx - 1) & 1);
+            tc_fence_after();
 #pragma unroll
             for (int sc = 0; sc < NGRP; ++sc) {
-                uint32_t acc[8];
+                uint32_t acc[8], ahn[8];
                 tmem_ld_32x32b_x8(taddr + sc * 8, acc);
-                uint4 cur[6];
+                tmem_ld_32x32b_x8(taddr + 64 + st * 64 + sc * 8, ahn);
+                uint4 cur[4];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) cur[i] = raw[i];
+                for (int i = 0; i < 4; ++i) cur[i] = raw[i];
                 if (sc < NGRP - 1) load_raw(sidx, sc + 1);
                 else if (sidx + 1 < T) load_raw(sidx + 1, 0);
-                float r[8], z[8], n[8], hn[8], hp[8], dout[8];
-                unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n); unpack8h(cur[3], hn);
-                unpack8(cur[4], hp); unpack8(cur[5], dout);
+                float r[8], z[8], n[8], hp[8], dout[8], bh[8];
+                unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n);
+                unpack8(*reinterpret_cast<const uint4*>(hp_row + (cb + sc) * CHUNK_S), hp);
+                unpack8(cur[3], dout);
+                {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bhn_s + ub + sc * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bhn_s + ub + sc * 8 + 4);
+                    bh[0] = b0.x; bh[1] = b0.y; bh[2] = b0.z; bh[3] = b0.w; bh[4] = b1.x; bh[5] = b1.y; bh[6] = b1.z; bh[7] = b1.w;
+                }
                 tmem_ld_wait();
                 float gr[8], gz[8], gn[8], ghn[8];
                 uint32_t carry[8];
@@ -493,12 +533,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     float dov = active ? dout[j] : 0.0f;
                     if (p.drop_bits) dov = ((dbits >> (sc * 8 + j)) & 1u) ? dov * dscale : 0.0f;
                     const float dh = __uint_as_float(acc[j]) + dov;
+                    const float hn = __uint_as_float(ahn[j]) + bh[j];
                     const float dn = dh * (1.0f - z[j]);
                     const float dz = dh * (hp[j] - n[j]);
                     gn[j] = dn * (1.0f - n[j] * n[j]);
                     gz[j] = dz * z[j] * (1.0f - z[j]);
                     ghn[j] = gn[j] * r[j];
-                    gr[j] = gn[j] * hn[j] * r[j] * (1.0f - r[j]);
+                    gr[j] = gn[j] * hn * r[j] * (1.0f - r[j]);
                     carry[j] = __float_as_uint(dh * z[j]);
                 }
                 const uint4 vr = pack8(gr), vz = pack8(gz), vn = pack8(gn), vh = pack8(ghn);
@@ -516,13 +557,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(ar_remote);
+            if (lane == 0) {
+                mbar_arrive(&hp_free[st]);                 // this warp is done with the stage's h_{t-1} tile and hn buffer
+                mbar_arrive_cluster(ar_remote);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 0) tmem_dealloc_pair<64 * NT>(tmem_base);
+    if (warp == 0) tmem_dealloc_pair<256>(tmem_base);
 }
 
 // (B, T, C) fp32 mask (0 or 1/keep) -> one bit per element in the order the recurrence kernels read them,
@@ -579,7 +623,7 @@ __global__ void gen_drop_bits_kernel(uint8_t* __restrict__ bits, long long n_byt
     }
 }
 
-int rec_mode() {            // RS_REC_MODE: 0 = automatic, 1 = one CTA per tile (rec_bf16.cu), 2 = pair NT = 1, 3 = pair NT = 2
+int rec_mode() {            // RS_REC_MODE: 0 = automatic, 2 = NT = 1, 3 = NT = 2
     const char* e = getenv("RS_REC_MODE");
     return e ? atoi(e) : 0;
 }
@@ -588,19 +632,18 @@ int rec_mode() {            // RS_REC_MODE: 0 = automatic, 1 = one CTA per tile 
 
 namespace rs {
 
-// Tiles in flight per CTA pair, or 0 for the one-CTA-per-tile kernels of rec_bf16.cu (RS_REC_MODE=1: A/B comparisons only).
-// Measured on B200 (tools/pair_check.sh, ms per 500-step launch pair at B = 1024 / 8192):
+// Tiles in flight per CTA pair of the forward kernel.  Measured on B200 (ms per 500-step launch pair at 1024 / 8192 traces;
+// "one CTA per tile" = round 1's kernels, retired):
 //   forward : one CTA per tile 5.1 / 6.3   pair NT=1 2.7 / 6.3   pair NT=2 4.1 / 5.8
 //   backward: one CTA per tile 5.5 / 7.4   pair NT=1 2.9 / 6.9   pair NT=2 5.8 / 8.0
 // Forward: NT = 1 while every tile can have its own pair of SMs in both directions (<= 37 tiles), else NT = 2 (the MMA of one
-// tile runs under the epilogue of the other).  Backward: always NT = 1 -- the BPTT epilogue is bound by the latency of its
-// gate / h / d_out loads, which two waves of half-size CTAs hide better than two tiles on one register-capped CTA.
-int rec_pair_nt(int B, bool need_pair, bool backward) {
+// tile runs under the epilogue of the other).  The backward kernel is built for one tile per pair only: its epilogue is bound
+// by the latency of its gate / d_out loads, which two waves of half-size CTAs hide better than two tiles on one
+// register-capped CTA.  RS_REC_MODE=2 / 3 forces NT = 1 / 2 (tests run both).
+int rec_fwd_nt(int B) {
     const int mode = rec_mode();
-    if (mode == 1 && !need_pair) return 0;
     if (mode == 2) return 1;
     if (mode == 3) return 2;
-    if (backward) return 1;
     const int n_tiles = (B + 127) / 128;
     return (n_tiles * 4 <= 148) ? 1 : 2;
 }
@@ -637,30 +680,28 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const fl
     return 0;
 }
 
-int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, void* dG,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, int split, int B, int T, int nt,
-                 int pf_dist, cudaStream_t stream) {
+int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, const void* Whh,
+                 int whh_chunks, const float* b_hn, void* dG, const int* lengths, const void* drop_bits, const float* drop_scale,
+                 int split, int B, int T, int pf_dist, cudaStream_t stream) {
     BwdPairParams p = {};
-    p.pf_dist = pf_dist;
     p.d_out = static_cast<const uint8_t*>(d_out); p.dout_block_bytes = 2LL * H * 256;
     p.d_h_n = d_h_n; p.gates = static_cast<const uint8_t*>(gates);
     p.out = static_cast<const uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
     p.WhhT = static_cast<const uint8_t*>(WhhT);
+    p.Whh = static_cast<const uint8_t*>(Whh); p.whh_chunks = whh_chunks; p.b_hn = b_hn;
     p.dG = static_cast<uint8_t*>(dG); p.dg_block_bytes = 8LL * H * 256;
     p.lengths = lengths;
     p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale;
-    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.split = split ? 1 : 0;
-    const int pairs = (p.n_tiles + nt - 1) / nt;
-    const int smem = (1 + p.split) * W_BWD_BYTES + nt * A_BWD_BYTES + 128;
-    const dim3 grid(2 * pairs, 2);
-#define RS_LAUNCH_BWD(NT_, VL_)                                                                                         \
-    do {                                                                                                                \
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<NT_, VL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        rec_bwd_pair_kernel<NT_, VL_><<<grid, NUM_THREADS, smem, stream>>>(p);                                       \
-    } while (0)
-    if (nt == 1) { if (lengths) RS_LAUNCH_BWD(1, true); else RS_LAUNCH_BWD(1, false); }
-    else { if (lengths) RS_LAUNCH_BWD(2, true); else RS_LAUNCH_BWD(2, false); }
-#undef RS_LAUNCH_BWD
+    p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.split = split ? 1 : 0; p.pf_dist = pf_dist;
+    const int smem = (1 + p.split) * (W_BWD_BYTES + 16 * CHUNK_S) + A_BWD_BYTES + 2 * HP_BYTES + H * 4 + 256;
+    const dim3 grid(2 * p.n_tiles, 2);
+    if (lengths) {
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        rec_bwd_pair_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
+    } else {
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        rec_bwd_pair_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
+    }
     count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -151,7 +151,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
             out_drop = L.empty_tm(B, T, 2 * H, dev, zero_pads=False) if drop is not None else None
             d_bits, d_scale = drop if drop is not None else (None, None)
             h_n = torch.empty(2, B, H, device=dev)
-            gates = torch.empty(tiles, T, 2, 64, L.TILE, 8, device=dev, dtype=torch.bfloat16) if need_grad else None
+            gates = torch.empty(tiles, T, 2, 48, L.TILE, 8, device=dev, dtype=torch.bfloat16) if need_grad else None   # r | z | n
             rec_flops = 2.0 * B * T * 2 * 3 * H * H
             X = None
             if not padded_in:
@@ -176,7 +176,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
         ctx.lengths = lengths
         # save_for_backward (not ctx attributes): `out` is an OUTPUT of this node; holding it in a plain attribute
         # would create a reference cycle node -> out -> grad_fn -> node and keep gigabytes alive until the cycle GC runs
-        ctx.save_for_backward(out, gates, saved_in, whhT_img, wt_dgrad)
+        ctx.save_for_backward(out, gates, saved_in, whhT_img, wt_dgrad, whh_img, b_hn)
         if out_drop is not None:
             return out_drop, h_n
         return out, h_n
@@ -185,7 +185,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
     @_lib.on_tensor_device
     def backward(ctx, d_out, d_h_n):
         padded_in, B, T, Il, split = ctx.meta
-        out, gates, saved_in, whhT_img, wt_dgrad = ctx.saved_tensors
+        out, gates, saved_in, whhT_img, wt_dgrad, whh_img, b_hn = ctx.saved_tensors
         if gates is None:
             raise RuntimeError("GRULayerBF16Fn: forward ran without saving activations (nothing required grad)")
         dev = out.device
@@ -197,8 +197,8 @@ class GRULayerBF16Fn(torch.autograd.Function):
             dG = torch.empty(tiles, T + 2, 8 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
             with ktime("rec_bwd_pair_kernel", 2.0 * B * T * 2 * 3 * H * H):
                 d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
-                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(dG), _p(ctx.lengths),
-                          _p(d_bits), _p(d_scale), split, B, T, st)
+                _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(whh_img), whh_img.shape[1],
+                          _p(b_hn), _p(dG), _p(ctx.lengths), _p(d_bits), _p(d_scale), split, B, T, st)
             # ALL weight / bias gradients of the layer in one fused pass over dG (12 roles, see csrc/gemm_blk.cu):
             #   ih roles (dir, g in r,z,n): dG block ^T . X            -> dW_ih rows, bias sums of r, z, n
             #   hh roles (dir, g in r,z,hn): dG block ^T . h(t' -/+ 1) -> dW_hh rows, bias sum of hn
