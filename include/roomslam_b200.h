@@ -163,17 +163,23 @@ int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_r
  * NULL.
  * split = 1: every weight image holds a bf16 PAIR per weight, hi = bf16(w) then lo = bf16(w - hi), stacked along K
  * (whh_img: chunks [0, H/8) hi, [H/8, H/4) lo, then the layer-0 input chunks; whhT_img, wt_proj, wt_dgrad: K blocks hi
- * then lo); rs_rec_fwd_bf16 / rs_rec_bwd_bf16 take the same flag, rs_blk_gemm_nt simply runs the longer K. */
+ * then lo); rs_rec_fwd_bf16 / rs_rec_bwd_bf16 take the same flag, rs_blk_gemm_nt simply runs the longer K.
+ * wih_img [2][I/8][3H][8] bf16 (or NULL): W_ih as a resident B operand for the projection fused into the recurrence kernel
+ * (rs_rec_fwd_bf16 with X); whh_img then also carries the two input chunks, holding the folded bias only. */
 int rs_gru_pack_weights_bf16(const float* const* w, int H, int I, int split, void* whh_img, float* b_hn, float* bias_x,
-                             void* wt_proj, void* whhT_img, void* wt_dgrad, void* stream);
+                             void* wt_proj, void* whhT_img, void* wt_dgrad, void* wih_img, void* stream);
 /* ---- bf16 mode: persistent tcgen05 GRU recurrence (H = 128), tile-major activations --------------------------- */
 /* Forward of one bidirectional layer.  Layer 0: x (B, T, I <= 2) fp32, its projection rides on the tensor core:
  * Whh is then [2][18][384][8] bf16 with chunk 16 = per gate row (w_hi, w_hi, w_lo) per input and (b_hi, b_lo), chunk
- * 17 = 0.  Deeper layers: P tile-major (6H columns, bias folded in) and Whh [2][16][384][8].  The r and z rows of all
+ * 17 = 0.  Deeper layers, either: P tile-major (6H columns, bias folded in) and Whh [2][16][384][8]; or, with the
+ * projection FUSED into the recurrence (unsplit weights): X = the layer's tile-major input (2H columns), Wih
+ * [2][32][384][8] and Whh [2][18][384][8] whose chunk 16 holds only the bias (rs_gru_pack_weights_bf16 with wih_img) --
+ * P and the projection GEMM are then not needed at all.  The r and z rows of all
  * weights / biases carry the factor 1/2 of sigma(a) = tanh(a/2)/2 + 1/2.  b_hn [2][H], out tile-major (2H columns,
  * zero pad rows), gates [tiles][T][2][48][128][8] fp16 = r | z | n (NULL for inference; W_hn h + b_hn is NOT saved, the
  * backward kernel recomputes it), h_n [2][B][H] fp32. */
-int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh, const float* b_hn, void* out,
+int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* X, const void* Wih, const void* Whh,
+                    const float* b_hn, void* out,
                     void* gates, float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale,
                     void* out_drop, int split, int B, int T, void* stream);
 /* x (B, T, I <= 16) fp32 -> tile-major bf16 with 16 columns (zero padded): layer-0 input for rs_blk_wgrad. */

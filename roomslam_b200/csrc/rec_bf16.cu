@@ -48,14 +48,16 @@ int pf_dist_env(const char* name, int dflt) {
 
 }  // namespace
 
-extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* Whh,
+extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_cols, const void* X, const void* Wih, const void* Whh,
                                const float* b_hn, void* out, void* gates, float* h_n, const int* lengths,
                                const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T,
                                void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (B == 0) return 0;        // nothing to do: empty tensors carry null pointers
-    RS_REQUIRE((x != nullptr) != (P != nullptr), "rs_rec_fwd_bf16: exactly one of x (layer 0) and P (deeper layers) must be given");
+    RS_REQUIRE((x != nullptr) + (P != nullptr) + (X != nullptr) == 1,
+               "rs_rec_fwd_bf16: exactly one of x (layer 0), P (deeper layers, projected) and X (deeper layers, projection fused) must be given");
+    RS_REQUIRE(!X || (Wih && !split), "rs_rec_fwd_bf16: the fused projection needs Wih and plain (unsplit) weights");
     RS_REQUIRE(!x || (I >= 1 && I <= 2), "rs_rec_fwd_bf16: the MMA-fused input projection takes 1 or 2 input columns");
     RS_REQUIRE(!P || p_cols == 6 * H, "rs_rec_fwd_bf16: P must have 6H = %d columns", 6 * H);
     RS_REQUIRE(Whh && b_hn && out && h_n && B >= 0 && T >= 0, "rs_rec_fwd_bf16: bad arguments");
@@ -65,7 +67,7 @@ extern "C" int rs_rec_fwd_bf16(const float* x, int I, const void* P, int64_t p_c
     }
     RS_REQUIRE((drop_bits != nullptr) == (out_drop != nullptr) && (!drop_bits || drop_scale),
                "rs_rec_fwd_bf16: drop_bits, drop_scale and out_drop go together");
-    return rs::rec_fwd_pair(x, I, P, Whh, b_hn, out, gates, h_n, lengths, drop_bits, drop_scale, out_drop, split, B, T,
+    return rs::rec_fwd_pair(x, I, P, X, Wih, Whh, b_hn, out, gates, h_n, lengths, drop_bits, drop_scale, out_drop, split, B, T,
                             rs::rec_fwd_nt(B), pf_dist_env("RS_PF_DIST_FWD", 1), stream);
 }
 

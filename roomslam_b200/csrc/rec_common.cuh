@@ -69,9 +69,9 @@ __device__ __forceinline__ uint4 pack_x(const float* xp, int I) {
 #ifdef __CUDACC__
 // rec_pair.cu: the CTA-pair kernels behind rs_rec_fwd_bf16 / rs_rec_bwd_bf16 (same operands and results as rec_bf16.cu)
 int rec_fwd_nt(int B);                      // tiles in flight per pair of the forward kernel (1 or 2)
-int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T, int nt,
-                 int pf_dist, cudaStream_t stream);
+int rec_fwd_pair(const float* x, int I, const void* P, const void* X, const void* Wih, const void* Whh, const float* b_hn, void* out,
+                 void* gates, float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split,
+                 int B, int T, int nt, int pf_dist, cudaStream_t stream);
 int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const void* out, const void* WhhT, const void* Whh,
                  int whh_chunks, const float* b_hn, void* dG, const int* lengths, const void* drop_bits, const float* drop_scale,
                  int split, int B, int T, int pf_dist, cudaStream_t stream);

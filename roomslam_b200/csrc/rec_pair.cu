@@ -60,25 +60,48 @@ struct FwdPairParams {
     int B, T, n_tiles;
     int pf_dist;
     int split;                              // 1: Whh holds hi chunks then lo chunks (bf16 pairs per weight), K loop runs over both
+    const uint8_t* X; long long x_block_bytes;   // fused projection (kMode 2): this layer's INPUT, tile-major, 2H columns
+    const uint8_t* Wih;                          // [2][32][384][8] bf16: W_ih (r, z rows scaled by 1/2) as a resident B operand
 };
 
-template <int NT, bool kVarLen, bool kFusedX>
+// kMode 0: the input-side pre-activations come from HBM (P, written by the projection GEMM).
+// kMode 1: layer 0, the K = 2 input projection rides on the recurrence MMA as one more K = 16 step (hi / lo split operands).
+// kMode 2 (NT = 1): the K = 256 input projection of a deeper layer is FUSED: W_ih's rows of this CTA's hidden units stay in
+//   shared memory next to W_hh (96 + 54 KB; the master state is in registers in this mode), warp 1 bulk-copies the layer
+//   input X_t of the CTA's 64 rows one step ahead (32 KB, one buffer), and the issuer runs X_{t+1} . W_ih^T (+ the bias via the
+//   input chunk: a constant (1, 1) column against (b_hi, b_lo)) into the OTHER of two accumulator buffers while the epilogue
+//   of step t is still reading its own: the projection is off the recurrence's critical path, P (6 H bf16 per trace and step:
+//   6.3 GB written + read at the benchmark shape) and the projection GEMM launch disappear, and the epilogue has no global
+//   loads left at all.
+template <int NT, bool kVarLen, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_fwd_pair_kernel(const FwdPairParams p) {
+    constexpr bool kFusedX = (kMode != 0);                 // the n gate's input part arrives in its own accumulator columns
+    constexpr bool kProj = (kMode == 2);
+    static_assert(!kProj || NT == 1, "the fused projection needs the double-buffered accumulator of the one-tile mode");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_s = smem;                                   // [18 chunks][192 rows][16 B]
     const int n_hid = 16 * (1 + p.split);                  // hidden-state chunks of W: hi parts, then (split) lo parts
     const int n_chunks = n_hid + (kFusedX ? 2 : 0);
-    uint8_t* a_s = w_s + n_chunks * W_CHUNK;               // [NT][18 chunks][64 rows][16 B]  h_{t-1} | input columns
-    uint8_t* h32_s = a_s + NT * A_FWD_BYTES;               // [NT][32 chunks of 4 floats][64 rows][16 B]
-    float* bhn_s = reinterpret_cast<float*>(h32_s + NT * H32_BYTES);
+    uint8_t* wih_s = w_s + n_chunks * W_CHUNK;             // [32 chunks][192 rows][16 B]   (kProj)
+    uint8_t* a_s = wih_s + (kProj ? 32 * W_CHUNK : 0);     // [NT][18 chunks][64 rows][16 B]  h_{t-1} | input columns
+    uint8_t* h32_s = a_s + NT * A_FWD_BYTES;               // [NT][32 chunks of 4 floats][64 rows][16 B]   (NT = 2 only)
+    uint8_t* x_s = h32_s + (NT == 1 ? 0 : NT * H32_BYTES); // [32 chunks][64 rows][16 B]  X_t of this CTA's rows (kProj)
+    float* bhn_s = reinterpret_cast<float*>(x_s + (kProj ? 32 * CHUNK_S : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(bhn_s + H);
     uint64_t* w_full = bars;
     uint64_t* h_ready = bars + 1;               // [NT], the even CTA's copies collect the arrivals of BOTH CTAs
     uint64_t* acc_full = bars + 1 + NT;         // [NT], one per CTA (multicast commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NT);
+    uint64_t* x_full = bars + 1 + 2 * NT;       // kProj: this CTA's X tile landed (bulk-copy bytes)
+    uint64_t* x_rdy = x_full + 1;               // kProj, even CTA: both CTAs' X tiles landed (2 arrivals)
+    uint64_t* x_free = x_full + 2;              // kProj: the projection MMAs that read the X tile retired (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 3);
 
     using ES = EpiShape<NT>;
     constexpr int EPI_WARPS = ES::SLOT_WARPS, UPT = ES::UPT, NGRP = ES::NGRP;
+    // fp32 master copy of h (the blend must not re-round the state every step).  NT = 1: a thread owns 16 hidden units of
+    // one row for the whole sequence, so the master state is 16 REGISTERS and the 32 KB of shared memory go back to L1;
+    // NT = 2 (32 units per thread at the 96-register cap): shared memory.
+    constexpr bool kRegState = (NT == 1);
     const uint32_t rank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -93,26 +116,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             mbar_init(&h_ready[s], 2 * EPI_WARPS);
             mbar_init(&acc_full[s], 1);
         }
+        mbar_init(x_full, 1); mbar_init(x_rdy, 2); mbar_init(x_free, 1);
         fence_mbar_init();
     }
     if (warp == 0) {
-        tmem_alloc_pair<256 * NT>(tmem_slot);
+        tmem_alloc_pair<(kProj ? 512 : 256 * NT)>(tmem_slot);
         if (lane == 0) {            // this CTA's half of W_hh: per chunk the r, z, n rows of its 64 hidden units
-            mbar_expect_tx(w_full, n_chunks * W_CHUNK);
+            mbar_expect_tx(w_full, (n_chunks + (kProj ? 32 : 0)) * W_CHUNK);
             const uint8_t* src = p.Whh + (long long)dir * n_chunks * (384 * 16);
             for (int c = 0; c < n_chunks; ++c)
                 for (int g = 0; g < 3; ++g)
                     bulk_load(w_s + c * W_CHUNK + g * 1024, src + (long long)c * (384 * 16) + (g * 128 + rank * 64) * 16, 1024, w_full);
+            if (kProj) {
+                const uint8_t* srci = p.Wih + (long long)dir * 32 * (384 * 16);
+                for (int c = 0; c < 32; ++c)
+                    for (int g = 0; g < 3; ++g)
+                        bulk_load(wih_s + c * W_CHUNK + g * 1024, srci + (long long)c * (384 * 16) + (g * 128 + rank * 64) * 16, 1024, w_full);
+            }
         }
     }
     for (int i = threadIdx.x; i < H; i += blockDim.x) bhn_s[i] = p.b_hn[dir * H + i];
-    for (int i = threadIdx.x; i < NT * (A_FWD_BYTES + H32_BYTES) / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NT * (A_FWD_BYTES + (NT == 1 ? 0 : H32_BYTES)) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (fused_x && threadIdx.x < ROWS * NT) {           // input columns of the first step
         const int s = threadIdx.x / ROWS, rl = threadIdx.x % ROWS;
         const long long b = (long long)(tile0 + s) * 128 + rank * ROWS + rl;
-        *reinterpret_cast<uint4*>(a_s + s * A_FWD_BYTES + 16 * CHUNK_S + rl * 16) =
-            pack_x((s < n_slots && b < p.B) ? p.x + (b * T + (dir ? T - 1 : 0)) * p.I : nullptr, p.I);
+        *reinterpret_cast<uint4*>(a_s + s * A_FWD_BYTES + 16 * CHUNK_S + rl * 16) =      // kProj: the constant (1, 1) bias column only
+            pack_x((!kProj && s < n_slots && b < p.B) ? p.x + (b * T + (dir ? T - 1 : 0)) * p.I : nullptr, p.I);
     }
     fence_proxy_async();
     if (warp == 0) mbar_wait(w_full, 0);
@@ -137,6 +168,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256, 0, 0);
             constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
             const uint32_t w_addr = smem_u32(w_s);
+            if (kProj) {
+                const uint32_t a_addr = smem_u32(a_s), x_addr = smem_u32(x_s), wih_addr = smem_u32(wih_s);
+                // X_t . W_ih^T + bias into accumulator buffer `buf`: r | z -> [0, 128), the n gate's input part -> [192, 256)
+                auto issue_proj = [&](int step_x, uint32_t buf) {
+                    mbar_wait(x_rdy, step_x & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t d = tmem_base + buf * 256;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const uint64_t da = umma_desc_noswz(x_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            const uint32_t wk = wih_addr + k * 2 * W_CHUNK;
+                            tc_mma_bf16_pair(d, da, umma_desc_noswz(wk, W_CHUNK, 128), idesc256, k != 0);
+                            tc_mma_bf16_pair(d + 192, da, umma_desc_noswz(wk + 128 * 16, W_CHUNK, 128), idesc128, k != 0);
+                        }
+                        const uint64_t db = umma_desc_noswz(a_addr + 16 * CHUNK_S, CHUNK_S, 128);       // the (1, 1) column
+                        tc_mma_bf16_pair(d, db, umma_desc_noswz(w_addr + n_hid * W_CHUNK, W_CHUNK, 128), idesc256, 1u);
+                        tc_mma_bf16_pair(d + 192, db, umma_desc_noswz(w_addr + n_hid * W_CHUNK + 128 * 16, W_CHUNK, 128), idesc128, 1u);
+                        tc_commit_pair(x_free);             // the X tile may be refilled in both CTAs
+                    }
+                    __syncwarp();
+                };
+                issue_proj(0, 0);
+                for (int step = 0; step < T; ++step) {
+                    if (step > 0) {
+                        mbar_wait_cluster(&h_ready[0], (step - 1) & 1);
+                        tc_fence_after();
+                    }
+                    if (lane == 0) {                        // hidden part of step `step`, onto the projection already in the buffer
+                        const uint32_t d = tmem_base + (step & 1) * 256;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t da = umma_desc_noswz(a_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                            const uint32_t wk = w_addr + k * 2 * W_CHUNK;
+                            tc_mma_bf16_pair(d, da, umma_desc_noswz(wk, W_CHUNK, 128), idesc256, 1u);
+                            tc_mma_bf16_pair(d + 128, da, umma_desc_noswz(wk + 128 * 16, W_CHUNK, 128), idesc128, k != 0);
+                        }
+                        tc_commit_pair(&acc_full[0]);
+                    }
+                    __syncwarp();
+                    // the other buffer was last read by the epilogue of step - 1, which the h_ready wait above has seen finish
+                    if (step + 1 < T) issue_proj(step + 1, (step + 1) & 1);
+                }
+            } else
             for (int step = 0; step < T; ++step) {
                 for (int s = 0; s < n_slots; ++s) {
                     if (step > 0) {
@@ -170,6 +245,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 }
             }
         }
+    } else if (warp == 1 && kProj) {
+        // ===================== X tile producer (both CTAs): the layer input of the CTA's 64 rows, one step ahead ==========
+        // 32 pieces of 1 KB (one per 16-byte chunk column), one bulk copy per LANE: issued by one thread they would take
+        // longer to issue than a time step lasts
+        const uint32_t rdy_remote = mapa_cluster(smem_u32(x_rdy), 0);
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? (T - 1 - step) : step;
+            if (lane == 0) {
+                if (step > 0) mbar_wait(x_free, (step - 1) & 1);
+                mbar_expect_tx(x_full, 32 * CHUNK_S);
+            }
+            __syncwarp();
+            const uint8_t* src = p.X + ((long long)tile0 * (T + 2) + t + 1) * p.x_block_bytes + rank * 1024;
+            bulk_load(x_s + lane * CHUNK_S, src + (long long)lane * CHUNK_G, 1024, x_full);
+            if (lane == 0) {
+                if (step + 3 < T) {                        // L2 prefetch three steps ahead: the copies above then come from L2
+                    const int t3 = dir ? (T - 1 - step - 3) : step + 3;
+                    l2_prefetch(p.X + ((long long)tile0 * (T + 2) + t3 + 1) * p.x_block_bytes + (long long)(rank * 16) * CHUNK_G, 16 * CHUNK_G);
+                }
+                mbar_wait(x_full, step & 1);
+                mbar_arrive_cluster(rdy_remote);
+            }
+            __syncwarp();
+        }
     } else if (warp == 1) {
         // ===================== L2 prefetcher: this CTA pulls half of the next projection block =====================
         if (lane == 0 && !kFusedX && p.pf_dist > 0) {
@@ -194,13 +293,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         const long long b = (long long)tile * 128 + row;
         const bool live = b < p.B;
         const int ub = uh * 64 + wg * UPT;                 // first hidden unit of this thread
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 256 + wg * UPT;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 256 + wg * UPT;
         uint8_t* a_row = a_s + s * A_FWD_BYTES + rl * 16;
         uint8_t* h32_row = h32_s + s * H32_BYTES + rl * 16;
         const uint32_t hr_remote = mapa_cluster(smem_u32(&h_ready[s]), 0);
-        const float* xrow = p.x ? p.x + b * T * p.I : nullptr;
+        const float* xrow = (kMode == 1 && p.x) ? p.x + b * T * p.I : nullptr;
         const int len = (kVarLen && live) ? p.lengths[b] : T;
         const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+        float hreg[kRegState ? UPT : 1];
+#pragma unroll
+        for (int i = 0; i < (kRegState ? UPT : 1); ++i) hreg[i] = 0.0f;
 
         for (int step = 0; step < T; ++step) {
             const int t = dir ? (T - 1 - step) : step;
@@ -214,7 +316,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + ((ub / 8) & ~3)))
                         >> (((ub / 8) & 3) * 8);
             uint4 xnext = make_uint4(0, 0, 0, 0);
-            const bool write_x = fused_x && ub == 0 && step + 1 < T;
+            const bool write_x = kMode == 1 && ub == 0 && step + 1 < T;
+            const uint32_t taddr = taddr0 + (kProj ? (step & 1) * 256 : 0);
             if (write_x) xnext = pack_x(live ? xrow + (long long)(dir ? t - 1 : t + 1) * p.I : nullptr, p.I);
             uint4 pv[3];
             auto load_p = [&](int grp) {
@@ -242,7 +345,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
 #pragma unroll
                 for (int jp = 0; jp < 4; ++jp) {                        // two hidden units at a time keeps the live set small
                     float hv2[2], rv2[2], zv2[2], nv2[2], od2[2];
-                    const float2 ho2 = *reinterpret_cast<const float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8);
+                    const float2 ho2 = kRegState ? make_float2(hreg[grp * 8 + 2 * jp], hreg[grp * 8 + 2 * jp + 1])
+                                                 : *reinterpret_cast<const float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8);
                     const float2 bh2 = *reinterpret_cast<const float2*>(bhn_s + u0 + 2 * jp);
                     float2 pr2 = make_float2(0.f, 0.f), pz2 = pr2, pn2 = pr2;
                     if (!kFusedX) {
@@ -266,7 +370,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                         hv2[e] = h; rv2[e] = r; zv2[e] = z; nv2[e] = n;
                         od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
                     }
-                    *reinterpret_cast<float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8) = make_float2(hv2[0], hv2[1]);
+                    if (kRegState) { hreg[grp * 8 + 2 * jp] = hv2[0]; hreg[grp * 8 + 2 * jp + 1] = hv2[1]; }
+                    else *reinterpret_cast<float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8) = make_float2(hv2[0], hv2[1]);
                     wo[jp] = f2_to_bf2(hv2[0], hv2[1]);
                     wd[jp] = f2_to_bf2(od2[0], od2[1]);
                     wr[jp] = f2_to_h2(rv2[0], rv2[1]); wz[jp] = f2_to_h2(zv2[0], zv2[1]);
@@ -294,7 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                 // the peer's tensor core reads this CTA's W half until its last MMA retired
-    if (warp == 0) tmem_dealloc_pair<256 * NT>(tmem_base);
+    if (warp == 0) tmem_dealloc_pair<(kProj ? 512 : 256 * NT)>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -410,7 +515,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         }
     } else if (warp == 1) {
         // ===================== h_{t-1} tile producer (both CTAs) + hn issuer (even CTA) =====================
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
             const uint32_t wn_addr = smem_u32(wn_s);
             const uint32_t rdy_remote[2] = {mapa_cluster(smem_u32(&hp_rdy[0]), 0), mapa_cluster(smem_u32(&hp_rdy[1]), 0)};
@@ -419,31 +524,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 const uint32_t ph = (sidx >> 1) & 1;
                 const int t = dir ? sidx : (T - 1 - sidx);
                 const int t_prev = dir ? t + 1 : t - 1;
-                if (sidx >= 2) mbar_wait(&hp_free[st], ph ^ 1);        // the epilogue of step sidx - 2 is done with this stage
-                mbar_expect_tx(&hp_full[st], HP_BYTES);
-                const uint8_t* src = p.out + ((long long)tile * (T + 2) + t_prev + 1) * p.out_block_bytes + (long long)(dir * 16) * CHUNK_G + rank * 1024;
-                for (int c = 0; c < 16; ++c) bulk_load(hp_s + st * HP_BYTES + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, &hp_full[st]);
-                if (p.pf_dist > 0 && sidx + p.pf_dist < T) {           // optional L2 prefetch of a later step's gate / d_out blocks
-                    const int t2 = dir ? sidx + p.pf_dist : (T - 1 - sidx - p.pf_dist);
-                    l2_prefetch(p.gates + (((long long)tile * T + t2) * 2 + dir) * (48LL * CHUNK_G) + (long long)(rank * 24) * CHUNK_G, 24 * CHUNK_G);
-                    if (p.d_out) l2_prefetch(p.d_out + ((long long)tile * (T + 2) + t2 + 1) * p.dout_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
+                if (lane == 0) {
+                    if (sidx >= 2) mbar_wait(&hp_free[st], ph ^ 1);    // the epilogue of step sidx - 2 is done with this stage
+                    mbar_expect_tx(&hp_full[st], HP_BYTES);
                 }
-                mbar_wait(&hp_full[st], ph);
-                mbar_arrive_cluster(rdy_remote[st]);
-                if (rank == 0) {
-                    mbar_wait(&hp_rdy[st], ph);
-                    tc_fence_after();
-                    const uint32_t hp_addr = smem_u32(hp_s + st * HP_BYTES);
-                    for (int part = 0; part <= p.split; ++part) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint64_t da = umma_desc_noswz(hp_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
-                            const uint64_t db = umma_desc_noswz(wn_addr + (part * 16 + k * 2) * CHUNK_S, CHUNK_S, 128);
-                            tc_mma_bf16_pair(tmem_base + 64 + st * 64, da, db, idesc, (k | part) != 0);
-                        }
+                __syncwarp();
+                if (lane < 16) {                                       // 16 pieces of 1 KB, one bulk copy per lane
+                    const uint8_t* src = p.out + ((long long)tile * (T + 2) + t_prev + 1) * p.out_block_bytes + (long long)(dir * 16) * CHUNK_G + rank * 1024;
+                    bulk_load(hp_s + st * HP_BYTES + lane * CHUNK_S, src + (long long)lane * CHUNK_G, 1024, &hp_full[st]);
+                }
+                if (lane == 0) {
+                    if (p.pf_dist > 0 && sidx + p.pf_dist < T) {       // optional L2 prefetch of a later step's gate / d_out blocks
+                        const int t2 = dir ? sidx + p.pf_dist : (T - 1 - sidx - p.pf_dist);
+                        l2_prefetch(p.gates + (((long long)tile * T + t2) * 2 + dir) * (48LL * CHUNK_G) + (long long)(rank * 24) * CHUNK_G, 24 * CHUNK_G);
+                        if (p.d_out) l2_prefetch(p.d_out + ((long long)tile * (T + 2) + t2 + 1) * p.dout_block_bytes + (long long)(dir * 16 + rank * 8) * CHUNK_G, 8 * CHUNK_G);
                     }
-                    tc_commit_pair(&hn_full[st]);
+                    mbar_wait(&hp_full[st], ph);
+                    mbar_arrive_cluster(rdy_remote[st]);
+                    if (rank == 0) {
+                        mbar_wait(&hp_rdy[st], ph);
+                        tc_fence_after();
+                        const uint32_t hp_addr = smem_u32(hp_s + st * HP_BYTES);
+                        for (int part = 0; part <= p.split; ++part) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint64_t da = umma_desc_noswz(hp_addr + k * 2 * CHUNK_S, CHUNK_S, 128);
+                                const uint64_t db = umma_desc_noswz(wn_addr + (part * 16 + k * 2) * CHUNK_S, CHUNK_S, 128);
+                                tc_mma_bf16_pair(tmem_base + 64 + st * 64, da, db, idesc, (k | part) != 0);
+                            }
+                        }
+                        tc_commit_pair(&hn_full[st]);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -648,32 +761,37 @@ int rec_fwd_nt(int B) {
     return (n_tiles * 4 <= 148) ? 1 : 2;
 }
 
-int rec_fwd_pair(const float* x, int I, const void* P, const void* Whh, const float* b_hn, void* out, void* gates, float* h_n,
-                 const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split, int B, int T, int nt,
-                 int pf_dist, cudaStream_t stream) {
+int rec_fwd_pair(const float* x, int I, const void* P, const void* X, const void* Wih, const void* Whh, const float* b_hn, void* out,
+                 void* gates, float* h_n, const int* lengths, const void* drop_bits, const float* drop_scale, void* out_drop, int split,
+                 int B, int T, int nt, int pf_dist, cudaStream_t stream) {
     FwdPairParams p = {};
     p.x = x; p.I = I;
     p.P = static_cast<const uint8_t*>(P); p.p_block_bytes = 6LL * H * 256;
+    p.X = static_cast<const uint8_t*>(X); p.x_block_bytes = 2LL * H * 256; p.Wih = static_cast<const uint8_t*>(Wih);
     p.Whh = static_cast<const uint8_t*>(Whh); p.b_hn = b_hn;
     p.out = static_cast<uint8_t*>(out); p.out_block_bytes = 2LL * H * 256;
     p.gates = static_cast<uint8_t*>(gates); p.h_n = h_n; p.lengths = lengths;
     p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale; p.out_drop = static_cast<uint8_t*>(out_drop);
     p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.pf_dist = pf_dist; p.split = split ? 1 : 0;
+    const int mode = X ? 2 : (x ? 1 : 0);
+    if (mode == 2) nt = 1;                  // the fused projection runs one tile per pair (two waves above 37 tiles)
     const int pairs = (p.n_tiles + nt - 1) / nt;
-    const int smem = (16 * (1 + p.split) + (x ? 2 : 0)) * W_CHUNK + nt * (A_FWD_BYTES + H32_BYTES) + H * 4 + 128;
+    const int smem = (16 * (1 + p.split) + (mode ? 2 : 0)) * W_CHUNK + (mode == 2 ? 32 * W_CHUNK + 32 * CHUNK_S : 0) + nt * A_FWD_BYTES
+                     + (nt == 1 ? 0 : nt * H32_BYTES) + H * 4 + 256;
     const dim3 grid(2 * pairs, 2);
-#define RS_LAUNCH_FWD(NT_, VL_, FX_)                                                                                    \
+#define RS_LAUNCH_FWD(NT_, VL_, MODE_)                                                                                  \
     do {                                                                                                                \
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_pair_kernel<NT_, VL_, FX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        rec_fwd_pair_kernel<NT_, VL_, FX_><<<grid, NUM_THREADS, smem, stream>>>(p);                                  \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_pair_kernel<NT_, VL_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_fwd_pair_kernel<NT_, VL_, MODE_><<<grid, NUM_THREADS, smem, stream>>>(p);                                   \
     } while (0)
-#define RS_LAUNCH_FWD_X(NT_, VL_)                                                                                       \
+#define RS_LAUNCH_FWD_M(NT_, VL_)                                                                                       \
     do {                                                                                                                \
-        if (x) RS_LAUNCH_FWD(NT_, VL_, true); else RS_LAUNCH_FWD(NT_, VL_, false);                                      \
+        if (mode == 1) RS_LAUNCH_FWD(NT_, VL_, 1); else RS_LAUNCH_FWD(NT_, VL_, 0);                                     \
     } while (0)
-    if (nt == 1) { if (lengths) RS_LAUNCH_FWD_X(1, true); else RS_LAUNCH_FWD_X(1, false); }
-    else { if (lengths) RS_LAUNCH_FWD_X(2, true); else RS_LAUNCH_FWD_X(2, false); }
-#undef RS_LAUNCH_FWD_X
+    if (mode == 2) { if (lengths) RS_LAUNCH_FWD(1, true, 2); else RS_LAUNCH_FWD(1, false, 2); }
+    else if (nt == 1) { if (lengths) RS_LAUNCH_FWD_M(1, true); else RS_LAUNCH_FWD_M(1, false); }
+    else { if (lengths) RS_LAUNCH_FWD_M(2, true); else RS_LAUNCH_FWD_M(2, false); }
+#undef RS_LAUNCH_FWD_M
 #undef RS_LAUNCH_FWD
     count_launch();
     RS_CUDA_OK(cudaGetLastError());

@@ -13,6 +13,7 @@ weight gradients are fp32.  Tolerance against the fp32 CPU oracle: 2e-2 relative
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -133,10 +134,17 @@ class GRULayerBF16Fn(torch.autograd.Function):
             ws = [t.detach().float().contiguous() for t in (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
             bf = torch.bfloat16
             need_dx = padded_in and ctx.needs_input_grad[0]
-            whh_img = torch.empty(2, (H // 8) * (1 + split) + (0 if padded_in else 2), 3 * H, 8, device=dev, dtype=bf)
+            # deeper layers: from 38 tiles up (the launch no longer fits one wave of CTA pairs and runs against the HBM roof) the
+            # input projection is fused into the recurrence kernel: W_ih resident next to W_hh, no P in HBM, no projection GEMM
+            # (-1.3 ms per step at 8192 traces).  In the latency-bound regime below, the projection GEMM + P path is 2 % faster
+            # (6.74 vs 6.90 ms per step at 1024 traces), and split weights (W_ih hi + lo) would not fit.  RS_FUSE_PROJ=0/1 forces.
+            fuse_env = os.environ.get("RS_FUSE_PROJ")
+            fuse_proj = padded_in and not split and (fuse_env == "1" if fuse_env in ("0", "1") else tiles * 4 > 148)
+            whh_img = torch.empty(2, (H // 8) * (1 + split) + (2 if (not padded_in or fuse_proj) else 0), 3 * H, 8, device=dev, dtype=bf)
             b_hn = torch.empty(2, H, device=dev)
             bias_x = torch.empty(2, 3 * H, device=dev)
-            wt = torch.empty(6 * H // 128, (Il // 64) * (1 + split), 8, L.TILE, 8, device=dev, dtype=bf) if padded_in else None
+            wt = torch.empty(6 * H // 128, (Il // 64) * (1 + split), 8, L.TILE, 8, device=dev, dtype=bf) if (padded_in and not fuse_proj) else None
+            wih_img = torch.empty(2, Il // 8, 3 * H, 8, device=dev, dtype=bf) if fuse_proj else None
             whhT_img = torch.empty(2, (3 * H // 8) * (1 + split), H, 8, device=dev, dtype=bf)
             wt_dgrad = torch.empty(Il // 128, (6 * H // 64) * (1 + split), 8, L.TILE, 8, device=dev, dtype=bf) if need_dx else None
             if not padded_in and Il > 2:
@@ -145,7 +153,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                 raise _lib.RoomSlamError("bf16 mode: deeper layers take the 2H-column output of the layer below")
             wp = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in ws])
             _lib.call("rs_gru_pack_weights_bf16", ctypes.addressof(wp), H, Il, split, _p(whh_img), _p(b_hn), _p(bias_x), _p(wt), _p(whhT_img),
-                      _p(wt_dgrad), st)
+                      _p(wt_dgrad), _p(wih_img), st)
             # (the recurrence kernels zero the pad rows t' = 0, T + 1 of what they write)
             out = L.empty_tm(B, T, 2 * H, dev, zero_pads=False)
             out_drop = L.empty_tm(B, T, 2 * H, dev, zero_pads=False) if drop is not None else None
@@ -157,9 +165,15 @@ class GRULayerBF16Fn(torch.autograd.Function):
             if not padded_in:
                 x = xin.contiguous().float()
                 with ktime("rec_fwd_pair_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
-                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
+                    _lib.call("rs_rec_fwd_bf16", _p(x), Il, 0, 0, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
                               _p(d_bits), _p(d_scale), _p(out_drop), split, B, T, st)
                 saved_in = x
+            elif fuse_proj:
+                X = xin
+                with ktime("rec_fwd_pair_kernel", rec_flops + 2.0 * B * T * 6 * H * Il):
+                    _lib.call("rs_rec_fwd_bf16", 0, 0, 0, 0, _p(X), _p(wih_img), _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n),
+                              _p(lengths), _p(d_bits), _p(d_scale), _p(out_drop), 0, B, T, st)
+                saved_in = X
             else:
                 X = xin
                 P = torch.empty(tiles, T + 2, 6 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
@@ -167,7 +181,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                     _nt(X, Il, [8 * k for k in range(Il // 64)] * (1 + split), wt, 6, P, 6 * H, 0, bias_x.reshape(-1).contiguous(),
                         tiles * (T + 2), st)
                 with ktime("rec_fwd_pair_kernel", rec_flops):
-                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
+                    _lib.call("rs_rec_fwd_bf16", 0, 0, _p(P), 6 * H, 0, 0, _p(whh_img), _p(b_hn), _p(out), _p(gates), _p(h_n), _p(lengths),
                               _p(d_bits), _p(d_scale), _p(out_drop), split, B, T, st)
                 del P
                 saved_in = X
