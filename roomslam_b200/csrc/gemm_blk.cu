@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_kernel(const NtPara
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (rs::elect_one()) {
             int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t a_phase = 0;
             for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
                 const uint8_t* ablk = p.A + (long long)m * p.a_block_bytes;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_kernel(const NtPara
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     rs::mbar_wait(&full_bar[stage], phase);
                     rs::tc_fence_after();
-                    if (lane == 0) {
+                    if (rs::elect_one()) {
                         const uint32_t ss = rs::smem_u32(stages + stage * kStageBytes);
                         const uint32_t sa = kResident ? rs::smem_u32(a_res + (ab * 4 + kb) * PIECE_BYTES) : ss;
                         const uint32_t sb = kResident ? ss : ss + PIECE_BYTES;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_wres_kernel(const N
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (rs::elect_one()) {
             // W slice: the two 128-row pieces of every K block are interleaved chunk by chunk into 256-row chunk columns
             rs::mbar_expect_tx(w_full, p.k_blocks * 2 * PIECE_BYTES);
             for (int kb = 0; kb < p.k_blocks; ++kb)
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_wres_kernel(const N
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 rs::mbar_wait(&full_bar[stage], phase);
                 rs::tc_fence_after();
-                if (lane == 0) {
+                if (rs::elect_one()) {
                     const uint32_t sa = rs::smem_u32(stages + stage * PIECE_BYTES);
                     const uint32_t sb = w_addr + kb * 2 * PIECE_BYTES;
 #pragma unroll
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_tn_kernel(const TnPar
         const int i0 = split * p.blocks_per_split;
         const int i1 = min(total_blocks, i0 + p.blocks_per_split);
         if (warp == 0) {
-            if (lane == 0) {
+            if (rs::elect_one()) {
                 for (int i = i0; i < i1; ++i) {
                     const long long blk = (long long)(i / p.T) * p.Tp + 1 + (i % p.T);
                     rs::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_gemm_tn_kernel(const TnPar
             for (int i = i0; i < i1; ++i) {
                 rs::mbar_wait(&full_bar[stage], phase);
                 rs::tc_fence_after();
-                if (lane == 0) {
+                if (rs::elect_one()) {
                     const uint32_t sa = rs::smem_u32(stages + stage * stage_bytes);
                     const uint32_t sb = sa + 2 * PIECE_BYTES;
 #pragma unroll
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
         const int i1 = min(total_blocks, i0 + p.blocks_per_split);
         const int b_bytes = R.n_cols * 256;
         if (warp == 0) {
-            if (lane == 0) {
+            if (rs::elect_one()) {
                 for (int i = i0; i < i1; ++i) {
                     const long long blk = (long long)(i / p.T) * p.Tp + 1 + (i % p.T);
                     rs::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
             for (int i = i0; i < i1; ++i) {
                 rs::mbar_wait(&full_bar[stage], phase);
                 rs::tc_fence_after();
-                if (lane == 0) {
+                if (rs::elect_one()) {
                     const uint32_t sa = rs::smem_u32(stages + stage * stage_bytes);
                     const uint32_t sb = sa + 2 * PIECE_BYTES;
 #pragma unroll

@@ -83,7 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (rs::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -134,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 rs::mbar_wait(&full_bar[stage], phase);
                 rs::tc_fence_after();
-                if (lane == 0) {
+                if (rs::elect_one()) {
                     const uint32_t sa = rs::smem_u32(stage_base + stage * STAGE_BYTES);
                     const uint32_t sb = sa + TILE_A_BYTES;
 #pragma unroll

@@ -139,7 +139,7 @@ heatmap_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BinParams P, 
         const long long rows_left = n_traces - row0;
         const bool active = lane < rows_left;
         my_points += static_cast<unsigned long long>(rows_left < kTileRows ? rows_left : kTileRows) * seq_len;
-        if (lane == 0) {
+        if (rs::elect_one()) {
 #pragma unroll
             for (int s = 0; s < kStages; ++s) {
                 if (s < n_chunks) {
@@ -183,7 +183,7 @@ heatmap_tma_kernel(const __grid_constant__ CUtensorMap tmap, const BinParams P, 
 #pragma unroll
             for (int i = 0; i < kChunkPts; ++i) asm volatile("" ::"r"(cell[i]), "r"(inc[i]) : "memory");
             __syncwarp();
-            if (lane == 0 && c + kStages < n_chunks) {
+            if (c + kStages < n_chunks && rs::elect_one()) {       // elect.sync: ptxas issues the TMA without a per-lane loop
                 rs::mbar_expect_tx(&bar[s], kBufBytes);
                 rs::tma_load_2d_hint(buf0 + s * kBufBytes, &tmap, &bar[s], (c + kStages) * kChunkPts * 2, row0, policy);
             }

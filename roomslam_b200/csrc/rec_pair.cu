@@ -73,7 +73,9 @@ struct FwdPairParams {
 //   of step t is still reading its own: the projection is off the recurrence's critical path, P (6 H bf16 per trace and step:
 //   6.3 GB written + read at the benchmark shape) and the projection GEMM launch disappear, and the epilogue has no global
 //   loads left at all.
-template <int NT, bool kVarLen, int kMode>
+// kDrop: inter-layer dropout on this layer's output (drop_bits / out_drop given).  A template parameter, not a run-time
+// flag: the mask test, the scaled copy and its bf16 pack are ~3.5 of the epilogue's 24 instructions per (row, hidden unit).
+template <int NT, bool kVarLen, int kMode, bool kDrop>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_fwd_pair_kernel(const FwdPairParams p) {
     constexpr bool kFusedX = (kMode != 0);                 // the n gate's input part arrives in its own accumulator columns
     constexpr bool kProj = (kMode == 2);
@@ -159,7 +161,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         const long long off = ((long long)(tile0 + s) * (T + 2) + (pad ? T + 1 : 0)) * p.out_block_bytes
                               + (long long)(dir * 16 + c) * CHUNK_G + (rank * ROWS + rl) * 16;
         stg16(p.out + off, make_uint4(0, 0, 0, 0));
-        if (p.out_drop) stg16(p.out_drop + off, make_uint4(0, 0, 0, 0));
+        if (kDrop) stg16(p.out_drop + off, make_uint4(0, 0, 0, 0));
     }
 
     if (warp == 0) {
@@ -174,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 auto issue_proj = [&](int step_x, uint32_t buf) {
                     mbar_wait(x_rdy, step_x & 1);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t d = tmem_base + buf * 256;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
@@ -196,7 +198,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                         mbar_wait_cluster(&h_ready[0], (step - 1) & 1);
                         tc_fence_after();
                     }
-                    if (lane == 0) {                        // hidden part of step `step`, onto the projection already in the buffer
+                    if (elect_one()) {                      // hidden part of step `step`, onto the projection already in the buffer
                         const uint32_t d = tmem_base + (step & 1) * 256;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
@@ -218,7 +220,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                         mbar_wait_cluster(&h_ready[s], (step - 1) & 1);
                         tc_fence_after();
                     }
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t a_addr = smem_u32(a_s + s * A_FWD_BYTES);
                         const uint32_t d = tmem_base + s * 256;
                         for (int part = 0; part <= p.split; ++part) {     // split weights: h . W_hi^T + h . W_lo^T, same A tile
@@ -299,32 +301,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         const uint32_t hr_remote = mapa_cluster(smem_u32(&h_ready[s]), 0);
         const float* xrow = (kMode == 1 && p.x) ? p.x + b * T * p.I : nullptr;
         const int len = (kVarLen && live) ? p.lengths[b] : T;
-        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+        const float dscale = kDrop ? __ldg(p.drop_scale) : 1.0f;
         float hreg[kRegState ? UPT : 1];
 #pragma unroll
         for (int i = 0; i < (kRegState ? UPT : 1); ++i) hreg[i] = 0.0f;
 
+        // running pointers of this thread's pieces: one signed stride per time step instead of 64-bit index arithmetic
+        const int t_first = dir ? T - 1 : 0;
+        const long long blk_first = (long long)tile * (T + 2) + t_first + 1;
+        const long long o_first = blk_first * p.out_block_bytes + (long long)(dir * 16 + ub / 8) * CHUNK_G + row * 16;
+        const long long o_step = dir ? -p.out_block_bytes : p.out_block_bytes;
+        uint8_t* o_cur = p.out + o_first;
+        const long long od_delta = kDrop ? p.out_drop - p.out : 0;     // warp-uniform: the masked copy sits at the same offsets
+        const uint8_t* p_cur = kFusedX ? nullptr : p.P + blk_first * p.p_block_bytes + (long long)(dir * 48 + ub / 8) * CHUNK_G + row * 16;
+        const long long p_step = dir ? -p.p_block_bytes : p.p_block_bytes;
+        uint8_t* g_cur = p.gates ? p.gates + (((long long)tile * T + t_first) * 2 + dir) * (48LL * CHUNK_G) + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
+        const long long g_step = (dir ? -2 : 2) * (48LL * CHUNK_G);
+        const uint8_t* db_cur = kDrop ? p.drop_bits + (((long long)tile * T + t_first) * 128 + row) * 32 + dir * 16 + ((ub / 8) & ~3) : nullptr;
+        const long long db_step = dir ? -128 * 32 : 128 * 32;
+
+        // kMode 0: the projection block's pieces of this thread by per-thread loads, requested one chunk ahead of their use
+        uint4 pv[3];
+        auto load_p = [&](const uint8_t* base, int grp) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) pv[g] = ldg16(base + (long long)(g * 16 + grp) * CHUNK_G);
+        };
         for (int step = 0; step < T; ++step) {
             const int t = dir ? (T - 1 - step) : step;
             const bool active = !kVarLen || t < len;
-            const long long blk = (long long)tile * (T + 2) + t + 1;
-            const uint8_t* pblk = kFusedX ? nullptr : p.P + blk * p.p_block_bytes + (long long)(dir * 48 + ub / 8) * CHUNK_G + row * 16;
-            const long long o_off = blk * p.out_block_bytes + (long long)(dir * 16 + ub / 8) * CHUNK_G + row * 16;
-            uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * (48LL * CHUNK_G) + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
+            const uint8_t* pblk = p_cur;
+            uint8_t* const o_ptr = o_cur;
+            uint8_t* const od_ptr = o_cur + od_delta;
+            uint8_t* gblk = g_cur;
             uint32_t dbits = 0;
-            if (p.drop_bits)        // the mask bytes of this thread's units sit in one aligned 32-bit word
-                dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + ((ub / 8) & ~3)))
-                        >> (((ub / 8) & 3) * 8);
+            if (kDrop) {            // the mask bytes of this thread's units sit in one aligned 32-bit word
+                dbits = __ldg(reinterpret_cast<const uint32_t*>(db_cur)) >> (((ub / 8) & 3) * 8);
+                db_cur += db_step;
+            }
+            o_cur += o_step;
+            if (!kFusedX) p_cur += p_step;
+            if (g_cur) g_cur += g_step;
             uint4 xnext = make_uint4(0, 0, 0, 0);
             const bool write_x = kMode == 1 && ub == 0 && step + 1 < T;
             const uint32_t taddr = taddr0 + (kProj ? (step & 1) * 256 : 0);
             if (write_x) xnext = pack_x(live ? xrow + (long long)(dir ? t - 1 : t + 1) * p.I : nullptr, p.I);
-            uint4 pv[3];
-            auto load_p = [&](int grp) {
-#pragma unroll
-                for (int g = 0; g < 3; ++g) pv[g] = ldg16(pblk + (long long)(g * 16 + grp) * CHUNK_G);
-            };
-            if (!kFusedX) load_p(0);
+            if (!kFusedX) load_p(pblk, 0);
             mbar_wait(&acc_full[s], step & 1);
             tc_fence_after();
 #pragma unroll
@@ -338,7 +359,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 uint4 pc[3];
                 if (!kFusedX) {
                     pc[0] = pv[0]; pc[1] = pv[1]; pc[2] = pv[2];
-                    if (grp < NGRP - 1) load_p(grp + 1);
+                    if (grp < NGRP - 1) load_p(pblk, grp + 1);
                 }
                 tmem_ld_wait();
                 uint32_t wo[4], wd[4], wr[4], wz[4], wn[4];             // packed outputs: h, h (.) mask, r, z, n
@@ -362,27 +383,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                         const int j = 2 * jp + e;
                         const float ho = e ? ho2.y : ho2.x;
                         // the 1/2 of sigma(a) = 1/2 tanh(a/2) + 1/2 is folded into the r and z rows of the weights and biases
-                        const float r = fmaf(0.5f, tanh_fast(__uint_as_float(ar[j]) + (e ? pr2.y : pr2.x)), 0.5f);
-                        const float z = active ? fmaf(0.5f, tanh_fast(__uint_as_float(az[j]) + (e ? pz2.y : pz2.x)), 0.5f) : 1.0f;
+                        // (fused input columns: the accumulator already holds the whole pre-activation -- no `+ 0` left behind)
+                        const float ar_ = kFusedX ? __uint_as_float(ar[j]) : __uint_as_float(ar[j]) + (e ? pr2.y : pr2.x);
+                        const float az_ = kFusedX ? __uint_as_float(az[j]) : __uint_as_float(az[j]) + (e ? pz2.y : pz2.x);
+                        const float r = fmaf(0.5f, tanh_fast(ar_), 0.5f);
+                        const float z = active ? fmaf(0.5f, tanh_fast(az_), 0.5f) : 1.0f;
                         const float hn = __uint_as_float(an[j]) + (e ? bh2.y : bh2.x);
                         const float n = tanh_fast(fmaf(r, hn, e ? pn2.y : pn2.x));
                         const float h = active ? fmaf(z, ho - n, n) : ho;
                         hv2[e] = h; rv2[e] = r; zv2[e] = z; nv2[e] = n;
-                        od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
+                        if (kDrop) od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
                     }
                     if (kRegState) { hreg[grp * 8 + 2 * jp] = hv2[0]; hreg[grp * 8 + 2 * jp + 1] = hv2[1]; }
                     else *reinterpret_cast<float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8) = make_float2(hv2[0], hv2[1]);
                     wo[jp] = f2_to_bf2(hv2[0], hv2[1]);
-                    wd[jp] = f2_to_bf2(od2[0], od2[1]);
+                    if (kDrop) wd[jp] = f2_to_bf2(od2[0], od2[1]);
                     wr[jp] = f2_to_h2(rv2[0], rv2[1]); wz[jp] = f2_to_h2(zv2[0], zv2[1]);
                     wn[jp] = f2_to_h2(nv2[0], nv2[1]);
-                    if (step == T - 1 && live)
-                        *reinterpret_cast<float2*>(p.h_n + ((long long)dir * p.B + b) * H + u0 + 2 * jp) = make_float2(hv2[0], hv2[1]);
                 }
                 const uint4 o0 = make_uint4(wo[0], wo[1], wo[2], wo[3]);
                 *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK_S) = o0;      // next step's A operand, in place
-                stg16(p.out + o_off + (long long)grp * CHUNK_G, active ? o0 : make_uint4(0, 0, 0, 0));
-                if (p.out_drop) stg16(p.out_drop + o_off + (long long)grp * CHUNK_G, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+                stg16(o_ptr + (long long)grp * CHUNK_G, active ? o0 : make_uint4(0, 0, 0, 0));
+                if (kDrop) stg16(od_ptr + (long long)grp * CHUNK_G, make_uint4(wd[0], wd[1], wd[2], wd[3]));
                 if (gblk) {
                     stg16(gblk + (long long)(0 * 16 + grp) * CHUNK_G, make_uint4(wr[0], wr[1], wr[2], wr[3]));
                     stg16(gblk + (long long)(1 * 16 + grp) * CHUNK_G, make_uint4(wz[0], wz[1], wz[2], wz[3]));
@@ -394,6 +416,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             tc_fence_before();          // TMEM reads done before the next MMA overwrites the accumulator
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(hr_remote);
+        }
+        if (live) {                     // h_n: the fp32 master state after the last step (kept out of the step loop)
+            float* hn_row = p.h_n + ((long long)dir * p.B + b) * H + ub;
+#pragma unroll
+            for (int i = 0; i < UPT; i += 2)
+                *reinterpret_cast<float2*>(hn_row + i) =
+                    kRegState ? make_float2(hreg[i], hreg[i + 1])
+                              : *reinterpret_cast<const float2*>(h32_row + ((ub + i) / 4) * CHUNK_S + ((i >> 1) & 1) * 8);
         }
     }
     tc_fence_before();
@@ -431,8 +461,7 @@ struct BwdPairParams {
 };
 
 constexpr int HP_BYTES = 16 * CHUNK_S;                   // 16 KB: the h_{t-1} tile of this CTA's 64 rows (K-major A operand)
-
-template <bool kVarLen>
+template <bool kVarLen, bool kDrop>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_bwd_pair_kernel(const BwdPairParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int w_chunks = 48 * (1 + p.split), n_hid = 16 * (1 + p.split);
@@ -499,7 +528,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             for (int sidx = 0; sidx < T - 1; ++sidx) {     // the result of the last reverse step is unused
                 mbar_wait_cluster(a_ready, sidx & 1);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     for (int part = 0; part <= p.split; ++part) {
 #pragma unroll
                         for (int k = 0; k < 24; ++k) {
@@ -533,7 +562,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     const uint8_t* src = p.out + ((long long)tile * (T + 2) + t_prev + 1) * p.out_block_bytes + (long long)(dir * 16) * CHUNK_G + rank * 1024;
                     bulk_load(hp_s + st * HP_BYTES + lane * CHUNK_S, src + (long long)lane * CHUNK_G, 1024, &hp_full[st]);
                 }
-                if (lane == 0) {
+                if (elect_one()) {
                     if (p.pf_dist > 0 && sidx + p.pf_dist < T) {       // optional L2 prefetch of a later step's gate / d_out blocks
                         const int t2 = dir ? sidx + p.pf_dist : (T - 1 - sidx - p.pf_dist);
                         l2_prefetch(p.gates + (((long long)tile * T + t2) * 2 + dir) * (48LL * CHUNK_G) + (long long)(rank * 24) * CHUNK_G, 24 * CHUNK_G);
@@ -574,7 +603,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         uint8_t* a_row = a_s + rl * 16;
         const uint32_t ar_remote = mapa_cluster(smem_u32(a_ready), 0);
         const int len = (kVarLen && live) ? p.lengths[b] : T;
-        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+        const float dscale = kDrop ? __ldg(p.drop_scale) : 1.0f;
         // the carry z (.) dh lives in the TMEM accumulator; it starts as d_h_n
 #pragma unroll
         for (int sc = 0; sc < NGRP; ++sc) {
@@ -592,30 +621,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         }
         tmem_st_wait();
 
-        // raw 16-byte pieces of one chunk (8 units): r, z, n (fp16), d_out (bf16)
+        // r, z, n (fp16) and d_out (bf16) of the thread's two chunks (8 units each): per-thread global loads, requested one chunk
+        // ahead of their use
         uint4 raw[4];
         uint32_t dbits_next = 0;
-        auto load_raw = [&](int sidx, int sc) {
-            const int t = dir ? sidx : (T - 1 - sidx);
-            const long long blk = (long long)tile * (T + 2) + t + 1;
-            const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * (48LL * CHUNK_G) + (long long)(cb + sc) * CHUNK_G + row * 16;
+        // running pointers of this thread's pieces (one signed stride per time step instead of 64-bit index arithmetic)
+        const int t_first = dir ? 0 : T - 1;
+        const long long g_step = (dir ? 2 : -2) * (48LL * CHUNK_G);
+        const long long do_step = dir ? p.dout_block_bytes : -p.dout_block_bytes;
+        const long long dg_step = dir ? p.dg_block_bytes : -p.dg_block_bytes;
+        const uint8_t* g_ptr = p.gates + (((long long)tile * T + t_first) * 2 + dir) * (48LL * CHUNK_G) + (long long)cb * CHUNK_G + row * 16;
+        const uint8_t* do_ptr = p.d_out ? p.d_out + ((long long)tile * (T + 2) + t_first + 1) * p.dout_block_bytes
+                                                                   + (long long)(dir * 16 + cb) * CHUNK_G + row * 16 : nullptr;
+        const uint8_t* db_next = kDrop ? p.drop_bits + (((long long)tile * T + t_first) * 128 + row) * 32 + dir * 16 + (cb & ~3) : nullptr;
+        const long long db_step = dir ? 128 * 32 : -128 * 32;
+        uint8_t* dg_cur = p.dG + ((long long)tile * (T + 2) + t_first + 1) * p.dg_block_bytes + (long long)(dir * 64 + cb) * CHUNK_G + row * 16;
+        auto load_raw = [&](int sc) {                      // chunk sc of the step g_ptr / do_ptr stand at
 #pragma unroll
-            for (int g = 0; g < 3; ++g) raw[g] = ldg16(gblk + (long long)(g * 16) * CHUNK_G);
-            raw[3] = p.d_out ? ldg16(p.d_out + blk * p.dout_block_bytes + (long long)(dir * 16 + cb + sc) * CHUNK_G + row * 16)
-                             : make_uint4(0, 0, 0, 0);
-            if (sc == 0 && p.drop_bits)
-                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * 32 + dir * 16 + (cb & ~3)))
-                             >> ((cb & 3) * 8);
+            for (int g = 0; g < 3; ++g) raw[g] = ldg16(g_ptr + (long long)(g * 16 + sc) * CHUNK_G);
+            raw[3] = do_ptr ? ldg16(do_ptr + (long long)sc * CHUNK_G) : make_uint4(0, 0, 0, 0);
         };
-        load_raw(0, 0);
+        load_raw(0);
+        if (kDrop) dbits_next = __ldg(reinterpret_cast<const uint32_t*>(db_next)) >> ((cb & 3) * 8);
         for (int sidx = 0; sidx < T; ++sidx) {             // sidx-th reverse step = forward position T-1-sidx (dir 0)
             const int t = dir ? sidx : (T - 1 - sidx);
             const int st = sidx & 1;
-            const long long blk = (long long)tile * (T + 2) + t + 1;
             const bool active = !kVarLen || t < len;
-            uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 64 + cb) * CHUNK_G + row * 16;
+            uint8_t* dgblk = dg_cur;
+            dg_cur += dg_step;
             const uint8_t* hp_row = hp_s + st * HP_BYTES + rl * 16;
             const uint32_t dbits = dbits_next;
+            if (kDrop && sidx + 1 < T) {                   // next step's mask word: requested a whole step ahead
+                db_next += db_step;
+                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(db_next)) >> ((cb & 3) * 8);
+            }
             mbar_wait(&hn_full[st], (sidx >> 1) & 1);      // W_hn h_{t-1} of this step is in TMEM, the h_{t-1} tile in shared memory
             if (sidx > 0) mbar_wait(acc_full, (sidx - 1) & 1);
             tc_fence_after();
@@ -627,12 +666,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 uint4 cur[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) cur[i] = raw[i];
-                if (sc < NGRP - 1) load_raw(sidx, sc + 1);
-                else if (sidx + 1 < T) load_raw(sidx + 1, 0);
+                if (sc < NGRP - 1) load_raw(sc + 1);
+                else if (sidx + 1 < T) {
+                    g_ptr += g_step;
+                    if (do_ptr) do_ptr += do_step;
+                    load_raw(0);
+                }
                 float r[8], z[8], n[8], hp[8], dout[8], bh[8];
                 unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n);
-                unpack8(*reinterpret_cast<const uint4*>(hp_row + (cb + sc) * CHUNK_S), hp);
                 unpack8(cur[3], dout);
+                unpack8(*reinterpret_cast<const uint4*>(hp_row + (cb + sc) * CHUNK_S), hp);
                 {
                     const float4 b0 = *reinterpret_cast<const float4*>(bhn_s + ub + sc * 8);
                     const float4 b1 = *reinterpret_cast<const float4*>(bhn_s + ub + sc * 8 + 4);
@@ -644,15 +687,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float dov = active ? dout[j] : 0.0f;
-                    if (p.drop_bits) dov = ((dbits >> (sc * 8 + j)) & 1u) ? dov * dscale : 0.0f;
+                    if (kDrop) dov = ((dbits >> (sc * 8 + j)) & 1u) ? dov * dscale : 0.0f;
                     const float dh = __uint_as_float(acc[j]) + dov;
                     const float hn = __uint_as_float(ahn[j]) + bh[j];
-                    const float dn = dh * (1.0f - z[j]);
-                    const float dz = dh * (hp[j] - n[j]);
-                    gn[j] = dn * (1.0f - n[j] * n[j]);
-                    gz[j] = dz * z[j] * (1.0f - z[j]);
+                    const float omz = 1.0f - z[j];
+                    gn[j] = dh * omz * fmaf(-n[j], n[j], 1.0f);
+                    gz[j] = dh * (hp[j] - n[j]) * (z[j] * omz);
                     ghn[j] = gn[j] * r[j];
-                    gr[j] = gn[j] * hn * r[j] * (1.0f - r[j]);
+                    gr[j] = ghn[j] * (hn * (1.0f - r[j]));
                     carry[j] = __float_as_uint(dh * z[j]);
                 }
                 const uint4 vr = pack8(gr), vz = pack8(gz), vn = pack8(gn), vh = pack8(ghn);
@@ -779,10 +821,14 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* X, const void
     const int smem = (16 * (1 + p.split) + (mode ? 2 : 0)) * W_CHUNK + (mode == 2 ? 32 * W_CHUNK + 32 * CHUNK_S : 0) + nt * A_FWD_BYTES
                      + (nt == 1 ? 0 : nt * H32_BYTES) + H * 4 + 256;
     const dim3 grid(2 * pairs, 2);
+#define RS_LAUNCH_FWD_D(NT_, VL_, MODE_, DROP_)                                                                         \
+    do {                                                                                                                \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_pair_kernel<NT_, VL_, MODE_, DROP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_fwd_pair_kernel<NT_, VL_, MODE_, DROP_><<<grid, NUM_THREADS, smem, stream>>>(p);                            \
+    } while (0)
 #define RS_LAUNCH_FWD(NT_, VL_, MODE_)                                                                                  \
     do {                                                                                                                \
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_pair_kernel<NT_, VL_, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        rec_fwd_pair_kernel<NT_, VL_, MODE_><<<grid, NUM_THREADS, smem, stream>>>(p);                                   \
+        if (p.drop_bits) RS_LAUNCH_FWD_D(NT_, VL_, MODE_, true); else RS_LAUNCH_FWD_D(NT_, VL_, MODE_, false);          \
     } while (0)
 #define RS_LAUNCH_FWD_M(NT_, VL_)                                                                                       \
     do {                                                                                                                \
@@ -793,6 +839,7 @@ int rec_fwd_pair(const float* x, int I, const void* P, const void* X, const void
     else { if (lengths) RS_LAUNCH_FWD_M(2, true); else RS_LAUNCH_FWD_M(2, false); }
 #undef RS_LAUNCH_FWD_M
 #undef RS_LAUNCH_FWD
+#undef RS_LAUNCH_FWD_D
     count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
@@ -813,13 +860,14 @@ int rec_bwd_pair(const void* d_out, const float* d_h_n, const void* gates, const
     p.B = B; p.T = T; p.n_tiles = (B + 127) / 128; p.split = split ? 1 : 0; p.pf_dist = pf_dist;
     const int smem = (1 + p.split) * (W_BWD_BYTES + 16 * CHUNK_S) + A_BWD_BYTES + 2 * HP_BYTES + H * 4 + 256;
     const dim3 grid(2 * p.n_tiles, 2);
-    if (lengths) {
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        rec_bwd_pair_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
-    } else {
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        rec_bwd_pair_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
-    }
+#define RS_LAUNCH_BWD(VL_, DROP_)                                                                                       \
+    do {                                                                                                                \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_pair_kernel<VL_, DROP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_bwd_pair_kernel<VL_, DROP_><<<grid, NUM_THREADS, smem, stream>>>(p);                                        \
+    } while (0)
+    if (lengths) { if (p.drop_bits) RS_LAUNCH_BWD(true, true); else RS_LAUNCH_BWD(true, false); }
+    else { if (p.drop_bits) RS_LAUNCH_BWD(false, true); else RS_LAUNCH_BWD(false, false); }
+#undef RS_LAUNCH_BWD
     count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

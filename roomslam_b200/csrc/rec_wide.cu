@@ -135,7 +135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
     }
 
     if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {      // (elect.sync, not lane == 0: ptxas then issues the bulk copies without a per-instruction ELECT loop)
             // the producer runs about one time step ahead of the epilogue: prefetching step + 2 puts ~2 steps between the
             // HBM read and its use (this CTA's half of the projection block: 48 of the 96 chunks of its direction)
             auto prefetch = [&](int step) {
@@ -166,7 +166,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     mbar_wait(&rb->full[st], ph);
                     mbar_wait(&rb->peer_full[st], ph);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {      // back-to-back UTCHMMA (a lane == 0 guard costs an ELECT loop of ~13 instructions per MMA)
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
                             const int ks = sidx * 2 + kk;
@@ -370,7 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
     }
 
     if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // saved gates (4 x 32 chunks), h_{t-1} and d_out (32 chunks each) of the reverse step two ahead: this CTA's half
             auto prefetch = [&](int sidx) {
                 const int s2 = sidx + 2;
@@ -400,7 +400,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     mbar_wait(&rb->full[st], ph);
                     mbar_wait(&rb->peer_full[st], ph);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < 6; ++kk) {
                             const int ks = sg * 6 + kk;
