@@ -77,7 +77,9 @@ __device__ __forceinline__ void ring_relay(RingBars* rb, long long total, int NS
     }
 }
 
-template <bool kFusedX>
+// kVarLen / kDrop: packed variable-length traces / inter-layer dropout as template parameters (their selects, mask tests and the
+// masked copy cost instructions in the epilogue chain that bounds a time step even when unused)
+template <bool kFusedX, bool kVarLen, bool kDrop>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_fwd_wide_kernel(const FwdWideParams p) {
     // fp32 master copy of h: layer 0 needs all 512 TMEM columns for its accumulators (r | z | W_hn h | W_in x), so the state
     // lives in shared memory; deeper layers keep it in the 128 spare TMEM columns (64 KB of shared memory less: the L1 cache
@@ -131,7 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         const long long off = ((long long)tile * (T + 2) + (pad ? T + 1 : 0)) * p.out_block_bytes
                               + (long long)(dir * (HW / 8) + c) * CHUNK_G + (rank * ROWS + rl) * 16;
         stg16(p.out + off, make_uint4(0, 0, 0, 0));
-        if (p.out_drop) stg16(p.out_drop + off, make_uint4(0, 0, 0, 0));
+        if (kDrop) stg16(p.out_drop + off, make_uint4(0, 0, 0, 0));
     }
 
     if (warp == 1) {
@@ -208,26 +210,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         uint8_t* h32_row = h32_s + rl * 16;
         const uint32_t hr_remote = mapa_cluster(smem_u32(h_ready), 0);
         const float* xrow = p.x ? p.x + b * T * p.I : nullptr;
-        const int len = (p.lengths && live) ? p.lengths[b] : T;
-        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+        const int len = (kVarLen && live) ? p.lengths[b] : T;
+        const float dscale = kDrop ? __ldg(p.drop_scale) : 1.0f;
         if (kTmemState) {                                  // h_0 = 0 in the TMEM-resident master state
             uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int grp = 0; grp < NGRP; ++grp) tmem_st_32x32b_x8(taddr + 384 + grp * 8, zero);
             tmem_st_wait();
         }
+        // running pointers of this thread's pieces: one signed stride per time step instead of 64-bit index arithmetic
+        const int t_first = dir ? T - 1 : 0;
+        const long long blk_first = (long long)tile * (T + 2) + t_first + 1;
+        uint8_t* o_cur = p.out + blk_first * p.out_block_bytes + (long long)(dir * (HW / 8) + ub / 8) * CHUNK_G + row * 16;
+        const long long o_step = dir ? -p.out_block_bytes : p.out_block_bytes;
+        const long long od_delta = kDrop ? p.out_drop - p.out : 0;
+        const uint8_t* p_cur = kFusedX ? nullptr : p.P + blk_first * p.p_block_bytes + (long long)(dir * (3 * HW / 8) + ub / 8) * CHUNK_G + row * 16;
+        const long long p_step = dir ? -p.p_block_bytes : p.p_block_bytes;
+        uint8_t* g_cur = p.gates ? p.gates + (((long long)tile * T + t_first) * 2 + dir) * ((long long)(4 * HW / 8) * CHUNK_G)
+                                             + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
+        const long long g_step = (dir ? -2 : 2) * ((long long)(4 * HW / 8) * CHUNK_G);
+        const uint8_t* db_cur = kDrop ? p.drop_bits + (((long long)tile * T + t_first) * 128 + row) * (2 * HW / 8) + dir * (HW / 8) + ub / 8 : nullptr;
+        const long long db_step = dir ? -128 * (2 * HW / 8) : 128 * (2 * HW / 8);
 
         for (int step = 0; step < T; ++step) {
             const int t = dir ? (T - 1 - step) : step;
-            const bool active = t < len;
-            const long long blk = (long long)tile * (T + 2) + t + 1;
-            const uint8_t* pblk = kFusedX ? nullptr : p.P + blk * p.p_block_bytes + (long long)(dir * (3 * HW / 8) + ub / 8) * CHUNK_G + row * 16;
-            const long long o_off = blk * p.out_block_bytes + (long long)(dir * (HW / 8) + ub / 8) * CHUNK_G + row * 16;
-            uint8_t* gblk = p.gates ? p.gates + (((long long)tile * T + t) * 2 + dir) * ((long long)(4 * HW / 8) * CHUNK_G)
-                                          + (long long)(ub / 8) * CHUNK_G + row * 16 : nullptr;
+            const bool active = !kVarLen || t < len;
+            const uint8_t* pblk = p_cur;
+            uint8_t* const o_ptr = o_cur;
+            uint8_t* const od_ptr = o_cur + od_delta;
+            uint8_t* gblk = g_cur;
             uint32_t dbits = 0;
-            if (p.drop_bits)
-                dbits = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * (2 * HW / 8) + dir * (HW / 8) + ub / 8));
+            if (kDrop) {
+                dbits = __ldg(reinterpret_cast<const uint32_t*>(db_cur));
+                db_cur += db_step;
+            }
+            o_cur += o_step;
+            if (!kFusedX) p_cur += p_step;
+            if (g_cur) g_cur += g_step;
             uint4 xnext = make_uint4(0, 0, 0, 0);
             const bool write_x = kFusedX && ub == 0 && step + 1 < T;
             if (write_x) xnext = pack_x(live ? xrow + (long long)(dir ? t - 1 : t + 1) * p.I : nullptr, p.I);
@@ -274,28 +293,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                     for (int e = 0; e < 2; ++e) {
                         const int j = 2 * jp + e;
                         const float ho = e ? ho2.y : ho2.x;
-                        const float r = fmaf(0.5f, tanh_fast(__uint_as_float(ar[j]) + (e ? pr2.y : pr2.x)), 0.5f);
-                        const float z = active ? fmaf(0.5f, tanh_fast(__uint_as_float(az[j]) + (e ? pz2.y : pz2.x)), 0.5f) : 1.0f;
+                        const float ar_ = kFusedX ? __uint_as_float(ar[j]) : __uint_as_float(ar[j]) + (e ? pr2.y : pr2.x);
+                        const float az_ = kFusedX ? __uint_as_float(az[j]) : __uint_as_float(az[j]) + (e ? pz2.y : pz2.x);
+                        const float r = fmaf(0.5f, tanh_fast(ar_), 0.5f);
+                        const float z = active ? fmaf(0.5f, tanh_fast(az_), 0.5f) : 1.0f;
                         const float hn = __uint_as_float(an[j]) + (e ? bh2.y : bh2.x);
                         const float n = tanh_fast(fmaf(r, hn, e ? pn2.y : pn2.x));
                         const float h = active ? fmaf(z, ho - n, n) : ho;
                         hv2[e] = h; rv2[e] = r; zv2[e] = z; nv2[e] = n; hnv2[e] = hn;
-                        od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
+                        if (kDrop) od2[e] = (active && ((dbits >> (grp * 8 + j)) & 1u)) ? h * dscale : 0.0f;
                     }
                     if (kTmemState) { hnew[2 * jp] = __float_as_uint(hv2[0]); hnew[2 * jp + 1] = __float_as_uint(hv2[1]); }
                     else *reinterpret_cast<float2*>(h32_row + (u0 / 4 + jp / 2) * CHUNK_S + (jp & 1) * 8) = make_float2(hv2[0], hv2[1]);
                     wo[jp] = f2_to_bf2(hv2[0], hv2[1]);
-                    wd[jp] = f2_to_bf2(od2[0], od2[1]);
+                    if (kDrop) wd[jp] = f2_to_bf2(od2[0], od2[1]);
                     wr[jp] = f2_to_h2(rv2[0], rv2[1]); wz[jp] = f2_to_h2(zv2[0], zv2[1]);
                     wn[jp] = f2_to_h2(nv2[0], nv2[1]); wh[jp] = f2_to_h2(hnv2[0], hnv2[1]);
-                    if (step == T - 1 && live)
-                        *reinterpret_cast<float2*>(p.h_n + ((long long)dir * p.B + b) * HW + u0 + 2 * jp) = make_float2(hv2[0], hv2[1]);
                 }
                 if (kTmemState) tmem_st_32x32b_x8(taddr + 384 + grp * 8, hnew);
                 const uint4 o0 = make_uint4(wo[0], wo[1], wo[2], wo[3]);
                 *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK_S) = o0;
-                stg16(p.out + o_off + (long long)grp * CHUNK_G, active ? o0 : make_uint4(0, 0, 0, 0));
-                if (p.out_drop) stg16(p.out_drop + o_off + (long long)grp * CHUNK_G, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+                stg16(o_ptr + (long long)grp * CHUNK_G, active ? o0 : make_uint4(0, 0, 0, 0));
+                if (kDrop) stg16(od_ptr + (long long)grp * CHUNK_G, make_uint4(wd[0], wd[1], wd[2], wd[3]));
                 if (gblk) {
                     stg16(gblk + (long long)(0 * (HW / 8) + grp) * CHUNK_G, make_uint4(wr[0], wr[1], wr[2], wr[3]));
                     stg16(gblk + (long long)(1 * (HW / 8) + grp) * CHUNK_G, make_uint4(wz[0], wz[1], wz[2], wz[3]));
@@ -309,6 +328,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(hr_remote);
+        }
+        // h_n: the fp32 master state after the last step (kept out of the step loop)
+#pragma unroll
+        for (int grp = 0; grp < NGRP; ++grp) {
+            uint32_t hv[8];
+            if (kTmemState) {
+                tmem_ld_32x32b_x8(taddr + 384 + grp * 8, hv);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    const float2 v = *reinterpret_cast<const float2*>(h32_row + ((ub + grp * 8 + i) / 4) * CHUNK_S + ((i >> 1) & 1) * 8);
+                    hv[i] = __float_as_uint(v.x); hv[i + 1] = __float_as_uint(v.y);
+                }
+            }
+            if (live) {
+                float* dst = p.h_n + ((long long)dir * p.B + b) * HW + ub + grp * 8;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<uint4*>(dst + 4) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+            }
         }
     }
     tc_fence_before();
@@ -331,6 +370,7 @@ struct BwdWideParams {
     int nstage;
 };
 
+template <bool kVarLen, bool kDrop>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_bwd_wide_kernel(const BwdWideParams p) {
     const int NSTAGE = p.nstage;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -428,8 +468,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + wg * UPT;
         uint8_t* a_row = a_s + rl * 16;
         const uint32_t ar_remote = mapa_cluster(smem_u32(a_ready), 0);
-        const int len = (p.lengths && live) ? p.lengths[b] : T;
-        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
+        const int len = (kVarLen && live) ? p.lengths[b] : T;
+        const float dscale = kDrop ? __ldg(p.drop_scale) : 1.0f;
         constexpr int HC = HW / 8;                         // chunks per H columns
 #pragma unroll
         for (int sc = 0; sc < NGRP; ++sc) {
@@ -449,29 +489,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
 
         uint4 raw[6];
         uint32_t dbits_next = 0;
-        auto load_raw = [&](int sidx, int sc) {
-            const int fstep = T - 1 - sidx;
-            const int t = dir ? (T - 1 - fstep) : fstep;
-            const int t_prev = dir ? t + 1 : t - 1;
-            const long long blk = (long long)tile * (T + 2) + t + 1;
-            const long long blk_prev = (long long)tile * (T + 2) + t_prev + 1;
-            const uint8_t* gblk = p.gates + (((long long)tile * T + t) * 2 + dir) * ((long long)(4 * HC) * CHUNK_G) + (long long)(cb + sc) * CHUNK_G + row * 16;
+        // running pointers of this thread's pieces (one signed stride per time step instead of 64-bit index arithmetic)
+        const int t_first = dir ? 0 : T - 1;
+        const long long g_step = (dir ? 2 : -2) * ((long long)(4 * HC) * CHUNK_G);
+        const long long o_step = dir ? p.out_block_bytes : -p.out_block_bytes;
+        const long long do_step = dir ? p.dout_block_bytes : -p.dout_block_bytes;
+        const long long dg_step = dir ? p.dg_block_bytes : -p.dg_block_bytes;
+        const uint8_t* g_ptr = p.gates + (((long long)tile * T + t_first) * 2 + dir) * ((long long)(4 * HC) * CHUNK_G) + (long long)cb * CHUNK_G + row * 16;
+        // h_{t-1}: the block of the step before in forward time (t - 1 for the forward direction, t + 1 for the reverse one)
+        const uint8_t* hp_ptr = p.out + ((long long)tile * (T + 2) + t_first + (dir ? 1 : -1) + 1) * p.out_block_bytes
+                                + (long long)(dir * HC + cb) * CHUNK_G + row * 16;
+        const uint8_t* do_ptr = p.d_out ? p.d_out + ((long long)tile * (T + 2) + t_first + 1) * p.dout_block_bytes
+                                          + (long long)(dir * HC + cb) * CHUNK_G + row * 16 : nullptr;
+        const uint8_t* db_next = kDrop ? p.drop_bits + (((long long)tile * T + t_first) * 128 + row) * (2 * HC) + dir * HC + cb : nullptr;
+        const long long db_step = dir ? 128 * (2 * HC) : -128 * (2 * HC);
+        uint8_t* dg_cur = p.dG + ((long long)tile * (T + 2) + t_first + 1) * p.dg_block_bytes + (long long)(dir * 4 * HC + cb) * CHUNK_G + row * 16;
+        auto load_raw = [&](int sc) {                      // chunk sc of the step the pointers stand at
 #pragma unroll
-            for (int g = 0; g < 4; ++g) raw[g] = ldg16(gblk + (long long)(g * HC) * CHUNK_G);
-            raw[4] = ldg16(p.out + blk_prev * p.out_block_bytes + (long long)(dir * HC + cb + sc) * CHUNK_G + row * 16);
-            raw[5] = p.d_out ? ldg16(p.d_out + blk * p.dout_block_bytes + (long long)(dir * HC + cb + sc) * CHUNK_G + row * 16)
-                             : make_uint4(0, 0, 0, 0);
-            if (sc == 0 && p.drop_bits)
-                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(p.drop_bits + (((long long)tile * T + t) * 128 + row) * (2 * HC) + dir * HC + cb));
+            for (int g = 0; g < 4; ++g) raw[g] = ldg16(g_ptr + (long long)(g * HC + sc) * CHUNK_G);
+            raw[4] = ldg16(hp_ptr + (long long)sc * CHUNK_G);
+            raw[5] = do_ptr ? ldg16(do_ptr + (long long)sc * CHUNK_G) : make_uint4(0, 0, 0, 0);
         };
-        load_raw(0, 0);
+        load_raw(0);
+        if (kDrop) dbits_next = __ldg(reinterpret_cast<const uint32_t*>(db_next));
         for (int sidx = 0; sidx < T; ++sidx) {
-            const int fstep = T - 1 - sidx;
-            const int t = dir ? (T - 1 - fstep) : fstep;
-            const long long blk = (long long)tile * (T + 2) + t + 1;
-            const bool active = t < len;
-            uint8_t* dgblk = p.dG + blk * p.dg_block_bytes + (long long)(dir * 4 * HC + cb) * CHUNK_G + row * 16;
+            const int t = dir ? sidx : (T - 1 - sidx);
+            const bool active = !kVarLen || t < len;
+            uint8_t* dgblk = dg_cur;
+            dg_cur += dg_step;
             const uint32_t dbits = dbits_next;
+            if (kDrop && sidx + 1 < T) {                   // next step's mask word: requested a whole step ahead
+                db_next += db_step;
+                dbits_next = __ldg(reinterpret_cast<const uint32_t*>(db_next));
+            }
             if (sidx > 0) {
                 mbar_wait(acc_full, (sidx - 1) & 1);
                 tc_fence_after();
@@ -483,8 +533,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 uint4 cur[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) cur[i] = raw[i];
-                if (sc < NGRP - 1) load_raw(sidx, sc + 1);
-                else if (sidx + 1 < T) load_raw(sidx + 1, 0);
+                if (sc < NGRP - 1) load_raw(sc + 1);
+                else if (sidx + 1 < T) {
+                    g_ptr += g_step; hp_ptr += o_step;
+                    if (do_ptr) do_ptr += do_step;
+                    load_raw(0);
+                }
                 float r[8], z[8], n[8], hn[8], hp[8], dout[8];
                 unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n); unpack8h(cur[3], hn);
                 unpack8(cur[4], hp); unpack8(cur[5], dout);
@@ -494,14 +548,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float dov = active ? dout[j] : 0.0f;
-                    if (p.drop_bits) dov = ((dbits >> (sc * 8 + j)) & 1u) ? dov * dscale : 0.0f;
+                    if (kDrop) dov = ((dbits >> (sc * 8 + j)) & 1u) ? dov * dscale : 0.0f;
                     const float dh = __uint_as_float(acc[j]) + dov;
-                    const float dn = dh * (1.0f - z[j]);
-                    const float dz = dh * (hp[j] - n[j]);
-                    gn[j] = dn * (1.0f - n[j] * n[j]);
-                    gz[j] = dz * z[j] * (1.0f - z[j]);
+                    const float omz = 1.0f - z[j];
+                    gn[j] = dh * omz * fmaf(-n[j], n[j], 1.0f);
+                    gz[j] = dh * (hp[j] - n[j]) * (z[j] * omz);
                     ghn[j] = gn[j] * r[j];
-                    gr[j] = gn[j] * hn[j] * r[j] * (1.0f - r[j]);
+                    gr[j] = ghn[j] * (hn[j] * (1.0f - r[j]));
                     carry[j] = __float_as_uint(dh * z[j]);
                 }
                 const uint4 vr = pack8(gr), vz = pack8(gz), vn = pack8(gn), vh = pack8(ghn);
@@ -565,13 +618,19 @@ extern "C" int rs_rec_fwd_bf16_wide(const float* x, int I, const void* P, const 
     p.nstage = ring_stages(x ? "RS_WIDE_STAGES_FWD0" : "RS_WIDE_STAGES_FWD", 4, x ? 5 : 7);
     const int smem = p.nstage * WSTAGE + (x ? H32_BYTES : 0) + A_FWD_BYTES + HW * 4 + (int)sizeof(RingBars) + 64;
     const dim3 grid(2 * p.n_tiles, 2);
-    if (x) {
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        rec_fwd_wide_kernel<true><<<grid, NUM_THREADS, smem, stream>>>(p);
-    } else {
-        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        rec_fwd_wide_kernel<false><<<grid, NUM_THREADS, smem, stream>>>(p);
-    }
+#define RS_LAUNCH_FWDW(FX_, VL_, DROP_)                                                                                 \
+    do {                                                                                                                \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_fwd_wide_kernel<FX_, VL_, DROP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_fwd_wide_kernel<FX_, VL_, DROP_><<<grid, NUM_THREADS, smem, stream>>>(p);                                   \
+    } while (0)
+#define RS_LAUNCH_FWDW_V(FX_)                                                                                           \
+    do {                                                                                                                \
+        if (lengths) { if (drop_bits) RS_LAUNCH_FWDW(FX_, true, true); else RS_LAUNCH_FWDW(FX_, true, false); }         \
+        else { if (drop_bits) RS_LAUNCH_FWDW(FX_, false, true); else RS_LAUNCH_FWDW(FX_, false, false); }               \
+    } while (0)
+    if (x) RS_LAUNCH_FWDW_V(true); else RS_LAUNCH_FWDW_V(false);
+#undef RS_LAUNCH_FWDW_V
+#undef RS_LAUNCH_FWDW
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
@@ -598,8 +657,14 @@ extern "C" int rs_rec_bwd_bf16_wide(const void* d_out, const float* d_h_n, const
     p.B = B; p.T = T; p.n_tiles = (B + 127) / 128;
     p.nstage = ring_stages("RS_WIDE_STAGES_BWD", 4, 5);
     const int smem = p.nstage * WSTAGE + A_BWD_BYTES + (int)sizeof(RingBars) + 64;
-    RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rec_bwd_wide_kernel<<<dim3(2 * p.n_tiles, 2), NUM_THREADS, smem, stream>>>(p);
+#define RS_LAUNCH_BWDW(VL_, DROP_)                                                                                      \
+    do {                                                                                                                \
+        RS_CUDA_OK(cudaFuncSetAttribute(rec_bwd_wide_kernel<VL_, DROP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        rec_bwd_wide_kernel<VL_, DROP_><<<dim3(2 * p.n_tiles, 2), NUM_THREADS, smem, stream>>>(p);                      \
+    } while (0)
+    if (lengths) { if (drop_bits) RS_LAUNCH_BWDW(true, true); else RS_LAUNCH_BWDW(true, false); }
+    else { if (drop_bits) RS_LAUNCH_BWDW(false, true); else RS_LAUNCH_BWDW(false, false); }
+#undef RS_LAUNCH_BWDW
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;
