@@ -138,6 +138,12 @@ int rs_adamw_step_f32(float* p, const float* g, float* m, float* v, int64_t n, f
  * the 64 columns starting at chunk a_kchunk[kb] (HOST array); W is pre-tiled [n_tiles][k_blocks][8][128][8] bf16. */
 int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W, int n_tiles, void* C,
                    int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks, void* stream);
+/* The same without bias, the result multiplied by an inter-layer dropout mask in the epilogue: C = (A . W^T) (.) mask, mask =
+ * drop_bits ([tiles][T][128][c_cols / 8] bytes, one bit per element: rs_pack_drop_mask / rs_gen_drop_bits) x *drop_scale;
+ * n_blocks = tiles * (T + 2).  The data gradient dX of a layer whose INPUT went through dropout (README.md:114). */
+int rs_blk_gemm_nt_drop(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W, int n_tiles, void* C,
+                        int64_t c_cols, int c_chunk0, int64_t n_blocks, const void* drop_bits, const float* drop_scale, int T,
+                        void* stream);
 /* C[c_row0[mt] + i, j] (fp32, ldc) += sum over blocks (tile, t' = 1..T) of A_blk[:, (a_mchunk[mt])*8 + i] *
  * B_blk'[:, b_chunk0*8 + j] with B_blk' = the block b_shift time rows away (b_broadcast != 0: B is ONE block used
  * for every (tile, t'), e.g. a column of ones for bias gradients); n_cols % 16 == 0.  HOST arrays. */

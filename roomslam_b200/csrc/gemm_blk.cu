@@ -33,6 +33,9 @@ struct NtParams {
     uint8_t* C;        long long c_block_bytes;  int c_chunk0;
     const float* bias;
     int n_blocks, n_tiles, k_blocks;
+    // optional dropout mask on C (the data gradient of a layer whose INPUT went through inter-layer dropout): one bit per
+    // element, [tile][T][128 rows][c_cols / 8 bytes] as the recurrence kernels read it; block m = tile * (T + 2) + t + 1
+    const uint8_t* drop_bits; const float* drop_scale; int drop_T; int drop_row_bytes;
 };
 
 constexpr int NT_THREADS = 320;            // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (2 per TMEM lane quadrant)
@@ -139,8 +142,15 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_kernel(const NtPara
         const int q = warp & 3, row = q * 32 + lane;
         const int chalf = (warp - 2) >> 2;              // which 64 of the 128 tile columns this warp converts
         int acc = 0; uint32_t acc_phase = 0;
+        const float dscale = p.drop_bits ? __ldg(p.drop_scale) : 1.0f;
         for (int m = blockIdx.x; m < p.n_blocks; m += gridDim.x) {
             uint8_t* cblk = p.C + (long long)m * p.c_block_bytes + row * 16;
+            const uint8_t* drow = nullptr;                  // this row's mask bytes of the block (pad rows t' = 0, T + 1: none)
+            if (p.drop_bits) {
+                const int tp = m % (p.drop_T + 2);
+                if (tp >= 1 && tp <= p.drop_T)
+                    drow = p.drop_bits + (((long long)(m / (p.drop_T + 2)) * p.drop_T + (tp - 1)) * 128 + row) * p.drop_row_bytes;
+            }
             for (int n = 0; n < p.n_tiles; ++n) {
                 rs::mbar_wait(&acc_full[acc], acc_phase);
                 rs::tc_fence_after();
@@ -149,7 +159,14 @@ __global__ void __launch_bounds__(NT_THREADS, 1) blk_gemm_nt_kernel(const NtPara
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t r[32];
                     rs::tmem_ld_32x32b_x32(taddr + c0, r);
+                    uint32_t mbits = 0xffffffffu;           // 4 chunks x 8 columns
+                    if (drow) mbits = __ldg(reinterpret_cast<const uint32_t*>(drow + p.c_chunk0 + n * 16 + chalf * 8 + c0 / 8));
                     rs::tmem_ld_wait();
+                    if (p.drop_bits) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            r[e] = ((mbits >> e) & 1u) ? __float_as_uint(__uint_as_float(r[e]) * dscale) : 0u;
+                    }
                     const float* bs = bias_s + n * 128 + chalf * 64 + c0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -573,9 +590,9 @@ int num_sms() {
 
 }  // namespace
 
-extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W,
-                              int n_tiles, void* C, int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks,
-                              void* stream_) {
+static int blk_gemm_nt_impl(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W,
+                            int n_tiles, void* C, int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks,
+                            const void* drop_bits, const float* drop_scale, int drop_T, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (rs::check_device_sm100()) return 3;
     if (n_blocks == 0) return 0;        // nothing to do: empty tensors carry null pointers
@@ -593,9 +610,15 @@ extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk
     p.C = static_cast<uint8_t*>(C); p.c_block_bytes = c_cols * 256; p.c_chunk0 = c_chunk0;
     p.bias = bias; p.n_blocks = (int)n_blocks; p.n_tiles = n_tiles; p.k_blocks = k_blocks;
     RS_REQUIRE(n_tiles * 128 <= NT_MAX_N, "rs_blk_gemm_nt: at most %d output columns", NT_MAX_N);
+    if (drop_bits) {
+        RS_REQUIRE(drop_scale && drop_T >= 1 && n_blocks % (drop_T + 2) == 0 && c_chunk0 % 4 == 0 && c_cols % 32 == 0 && !bias,
+                   "rs_blk_gemm_nt_drop: the mask needs drop_scale, whole tiles of T + 2 blocks, 32-column alignment and no bias");
+        p.drop_bits = static_cast<const uint8_t*>(drop_bits); p.drop_scale = drop_scale; p.drop_T = drop_T;
+        p.drop_row_bytes = (int)(c_cols / 8);
+    }
     const int grid = (int)(n_blocks < num_sms() ? n_blocks : num_sms());
     static const bool wres_off = getenv("RS_NT_WRES") && atoi(getenv("RS_NT_WRES")) == 0;
-    if (k_blocks <= 4 && n_tiles % 2 == 0 && n_tiles / 2 <= 8 && n_blocks >= 2 * num_sms() && !wres_off) {
+    if (k_blocks <= 4 && n_tiles % 2 == 0 && n_tiles / 2 <= 8 && n_blocks >= 2 * num_sms() && !wres_off && !drop_bits) {
         // weight-resident: one CTA per (group, 256-column W slice); groups walk the blocks together
         const int n_parts = n_tiles / 2;
         const int groups = num_sms() / n_parts;
@@ -616,6 +639,22 @@ extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk
     }
     RS_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int rs_blk_gemm_nt(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W,
+                              int n_tiles, void* C, int64_t c_cols, int c_chunk0, const float* bias, int64_t n_blocks,
+                              void* stream_) {
+    return blk_gemm_nt_impl(A, a_cols, a_kchunk, k_blocks, W, n_tiles, C, c_cols, c_chunk0, bias, n_blocks, nullptr, nullptr, 0, stream_);
+}
+
+// rs_blk_gemm_nt without bias whose output is multiplied by an inter-layer dropout mask in the epilogue: C = (A . W^T) (.) mask.
+// The data gradient of a layer whose input went through dropout -- masking it here (a throughput-bound epilogue) keeps the
+// mask tests out of the serial per-time-step chain of the BPTT kernel of the layer below.
+extern "C" int rs_blk_gemm_nt_drop(const void* A, int64_t a_cols, const int* a_kchunk, int k_blocks, const void* W,
+                                   int n_tiles, void* C, int64_t c_cols, int c_chunk0, int64_t n_blocks, const void* drop_bits,
+                                   const float* drop_scale, int T, void* stream_) {
+    RS_REQUIRE(drop_bits != nullptr, "rs_blk_gemm_nt_drop: drop_bits is required");
+    return blk_gemm_nt_impl(A, a_cols, a_kchunk, k_blocks, W, n_tiles, C, c_cols, c_chunk0, nullptr, n_blocks, drop_bits, drop_scale, T, stream_);
 }
 
 extern "C" int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const int* c_row0, int m_tiles,

@@ -258,6 +258,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             if (!kFusedX) load_p(0);
             mbar_wait(acc_full, step & 1);
             tc_fence_after();
+            uint4 last_o, last_d = make_uint4(0, 0, 0, 0), last_r, last_z, last_n, last_h;
 #pragma unroll
             for (int grp = 0; grp < NGRP; ++grp) {
                 const int u0 = ub + grp * 8;
@@ -313,13 +314,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 if (kTmemState) tmem_st_32x32b_x8(taddr + 384 + grp * 8, hnew);
                 const uint4 o0 = make_uint4(wo[0], wo[1], wo[2], wo[3]);
                 *reinterpret_cast<uint4*>(a_row + (u0 / 8) * CHUNK_S) = o0;
-                stg16(o_ptr + (long long)grp * CHUNK_G, active ? o0 : make_uint4(0, 0, 0, 0));
-                if (kDrop) stg16(od_ptr + (long long)grp * CHUNK_G, make_uint4(wd[0], wd[1], wd[2], wd[3]));
-                if (gblk) {
-                    stg16(gblk + (long long)(0 * (HW / 8) + grp) * CHUNK_G, make_uint4(wr[0], wr[1], wr[2], wr[3]));
-                    stg16(gblk + (long long)(1 * (HW / 8) + grp) * CHUNK_G, make_uint4(wz[0], wz[1], wz[2], wz[3]));
-                    stg16(gblk + (long long)(2 * (HW / 8) + grp) * CHUNK_G, make_uint4(wn[0], wn[1], wn[2], wn[3]));
-                    stg16(gblk + (long long)(3 * (HW / 8) + grp) * CHUNK_G, make_uint4(wh[0], wh[1], wh[2], wh[3]));
+                const uint4 so = active ? o0 : make_uint4(0, 0, 0, 0), sd = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                const uint4 sr = make_uint4(wr[0], wr[1], wr[2], wr[3]), sz = make_uint4(wz[0], wz[1], wz[2], wz[3]);
+                const uint4 sn = make_uint4(wn[0], wn[1], wn[2], wn[3]), sh = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                if (grp < NGRP - 1) {
+                    stg16(o_ptr + (long long)grp * CHUNK_G, so);
+                    if (kDrop) stg16(od_ptr + (long long)grp * CHUNK_G, sd);
+                    if (gblk) {
+                        stg16(gblk + (long long)(0 * (HW / 8) + grp) * CHUNK_G, sr);
+                        stg16(gblk + (long long)(1 * (HW / 8) + grp) * CHUNK_G, sz);
+                        stg16(gblk + (long long)(2 * (HW / 8) + grp) * CHUNK_G, sn);
+                        stg16(gblk + (long long)(3 * (HW / 8) + grp) * CHUNK_G, sh);
+                    }
+                } else {                // the last chunk's global stores wait until after the arrival (below)
+                    last_o = so; last_d = sd; last_r = sr; last_z = sz; last_n = sn; last_h = sh;
                 }
             }
             if (write_x) *reinterpret_cast<uint4*>(a_row + (HW / 8) * CHUNK_S) = xnext;
@@ -328,6 +336,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(hr_remote);
+            // the MEMBAR inside fence.proxy.async waits for the thread's global stores still in flight: the last chunk's are
+            // issued only now, under the wait for the next MMA (rec_pair.cu has the measurement)
+            stg16(o_ptr + (long long)(NGRP - 1) * CHUNK_G, last_o);
+            if (kDrop) stg16(od_ptr + (long long)(NGRP - 1) * CHUNK_G, last_d);
+            if (gblk) {
+                stg16(gblk + (long long)(0 * (HW / 8) + NGRP - 1) * CHUNK_G, last_r);
+                stg16(gblk + (long long)(1 * (HW / 8) + NGRP - 1) * CHUNK_G, last_z);
+                stg16(gblk + (long long)(2 * (HW / 8) + NGRP - 1) * CHUNK_G, last_n);
+                stg16(gblk + (long long)(3 * (HW / 8) + NGRP - 1) * CHUNK_G, last_h);
+            }
         }
         // h_n: the fp32 master state after the last step (kept out of the step loop)
 #pragma unroll
@@ -534,11 +552,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
 #pragma unroll
                 for (int i = 0; i < 6; ++i) cur[i] = raw[i];
                 if (sc < NGRP - 1) load_raw(sc + 1);
-                else if (sidx + 1 < T) {
-                    g_ptr += g_step; hp_ptr += o_step;
-                    if (do_ptr) do_ptr += do_step;
-                    load_raw(0);
-                }
                 float r[8], z[8], n[8], hn[8], hp[8], dout[8];
                 unpack8h(cur[0], r); unpack8h(cur[1], z); unpack8h(cur[2], n); unpack8h(cur[3], hn);
                 unpack8(cur[4], hp); unpack8(cur[5], dout);
@@ -572,6 +585,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(ar_remote);
+            // the next step's first chunk is requested after the arrival: no load in flight at the MEMBAR of fence.proxy.async
+            if (sidx + 1 < T) {
+                g_ptr += g_step; hp_ptr += o_step;
+                if (do_ptr) do_ptr += do_step;
+                load_raw(0);
+            }
         }
     }
     tc_fence_before();

@@ -317,9 +317,10 @@ class GRULayerFn(torch.autograd.Function):
                 dW_ih[3 * H:], dW_hh[1], db_ih[3 * H:], db_hh[3 * H:])
 
 
-def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None, split_weights=False):
+def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None, split_weights=False, mask_in_bptt=False):
     """Stack of bidirectional layers -> (out (B,T,2H) of the top layer, h_n (2L,B,H)), torch.nn.GRU semantics
-    (with `lengths`: those of a packed sequence)."""
+    (with `lengths`: those of a packed sequence).  mask_in_bptt (bf16 layers): the backward half of inter-layer dropout runs
+    inside the BPTT kernel of the producing layer instead of the dgrad epilogue of the consuming one (tests)."""
     layer_fn = layer_fn or GRULayerFn
     B, T = x.shape[0], x.shape[1]
     cur, padded_in, h_all = x, False, []
@@ -336,7 +337,9 @@ def gru_encoder(x, mask, num_layers, weights, layer_fn=None, lengths=None, split
     for l in range(num_layers):
         if bits_mode:
             drop = mask[l] if l < num_layers - 1 else None
-            cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths, drop, split_weights), None, *weights[8 * l: 8 * l + 8])
+            in_drop = mask[l - 1] if (l > 0 and not mask_in_bptt) else None   # the consumer masks its data gradient
+            cur, h_n = layer_fn.apply(cur, (padded_in, B, T, lengths, drop, split_weights, in_drop, mask_in_bptt), None,
+                                      *weights[8 * l: 8 * l + 8])
             padded_in = True
             h_all.append(h_n)
             continue

@@ -25,8 +25,14 @@ from .functional import _need_cuda, _p, _stream, ktime
 H = 128
 
 
-def _nt(A, a_cols, kchunks, W_tiled, n_tiles, C, c_cols, c_chunk0, bias, n_blocks, st):
+def _nt(A, a_cols, kchunks, W_tiled, n_tiles, C, c_cols, c_chunk0, bias, n_blocks, st, drop=None, T=0):
+    """drop = (bits, scale): the result is multiplied by that dropout mask in the epilogue (data gradient of a layer whose
+    input went through inter-layer dropout; no bias then)."""
     kch = L.int_array(kchunks)
+    if drop is not None:
+        _lib.call("rs_blk_gemm_nt_drop", _p(A), a_cols, ctypes.addressof(kch), len(kchunks), _p(W_tiled), n_tiles, _p(C), c_cols,
+                  c_chunk0, n_blocks, _p(drop[0]), _p(drop[1]), T, st)
+        return
     _lib.call("rs_blk_gemm_nt", _p(A), a_cols, ctypes.addressof(kch), len(kchunks), _p(W_tiled), n_tiles, _p(C), c_cols,
               c_chunk0, _p(bias), n_blocks, st)
 
@@ -103,11 +109,15 @@ def unpack_drop_bits(bits: torch.Tensor, scale: torch.Tensor, B: int) -> torch.T
 
 class GRULayerBF16Fn(torch.autograd.Function):
     """apply(xin, meta, mask, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r) -> (out tile-major bf16, h_n (2,B,H) fp32)
-    meta = (padded_in, B, T, lengths, drop).  padded_in False: xin is the raw trace batch (B, T, I) fp32 (layer 0);
-    True: xin is the tile-major bf16 output of the layer below.  drop = None or (bits, scale) from `drop_bits_from_mask` /
-    `gen_drop_bits`: inter-layer dropout on THIS layer's output -- the returned sequence is then out (.) mask (written by
-    the recurrence kernel next to out) and backward masks the incoming gradient inside the BPTT kernel.  `mask` (the fp32
-    path's float mask on the layer INPUT) must be None here."""
+    meta = (padded_in, B, T, lengths, drop, split, in_drop).  padded_in False: xin is the raw trace batch (B, T, I) fp32
+    (layer 0); True: xin is the tile-major bf16 output of the layer below.  drop = None or (bits, scale) from
+    `drop_bits_from_mask` / `gen_drop_bits`: inter-layer dropout on THIS layer's output -- the returned sequence is then
+    out (.) mask (written by the recurrence kernel next to out).  Its backward half belongs to the CONSUMER: the layer above
+    gets the same pair as in_drop and multiplies its data gradient dX by the mask in the epilogue of the dgrad GEMM (a
+    throughput-bound kernel), so the gradient arriving here is already masked and the mask tests stay out of the serial
+    per-time-step chain of the BPTT kernel (-0.5 ms per step at 8192 traces).  meta[7] = True restores in-kernel masking of
+    the incoming gradient (a caller that feeds this layer's output to something else than the next layer).  `mask` (the
+    fp32 path's float mask on the layer INPUT) must be None here."""
 
     @staticmethod
     @_lib.on_tensor_device
@@ -120,6 +130,8 @@ class GRULayerBF16Fn(torch.autograd.Function):
         lengths = meta[3] if len(meta) > 3 else None
         drop = meta[4] if len(meta) > 4 else None
         split = 1 if (len(meta) > 5 and meta[5]) else 0      # weights as bf16 pairs hi + lo (small batches; csrc/pack_w.cu)
+        ctx.in_drop = meta[6] if len(meta) > 6 else None     # mask on this layer's INPUT: applied to dX in backward
+        ctx.mask_d_out = bool(meta[7]) if len(meta) > 7 else False
         if mask is not None:
             raise _lib.RoomSlamError("GRULayerBF16Fn: pass dropout as packed bits on the producing layer (meta[4]), not as a float mask")
         if w_hh.shape[1] != H:
@@ -210,7 +222,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
             d_h_n = d_h_n.contiguous().float() if d_h_n is not None else None
             dG = torch.empty(tiles, T + 2, 8 * H // 8, L.TILE, 8, device=dev, dtype=torch.bfloat16)
             with ktime("rec_bwd_pair_kernel", 2.0 * B * T * 2 * 3 * H * H):
-                d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
+                d_bits, d_scale = ctx.drop if (ctx.drop is not None and ctx.mask_d_out) else (None, None)
                 _lib.call("rs_rec_bwd_bf16", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(whhT_img), _p(whh_img), whh_img.shape[1],
                           _p(b_hn), _p(dG), _p(ctx.lengths), _p(d_bits), _p(d_scale), split, B, T, st)
             # ALL weight / bias gradients of the layer in one fused pass over dG (12 roles, see csrc/gemm_blk.cu):
@@ -258,7 +270,7 @@ class GRULayerBF16Fn(torch.autograd.Function):
                     wt = wt_dgrad                                                  # [Il/128][12][8][128][8]
                     kch = [d * 64 + g * 16 + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in (0, 1)]
                     with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * H * Il):
-                        _nt(dG, 8 * H, kch * (1 + split), wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
+                        _nt(dG, 8 * H, kch * (1 + split), wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st, ctx.in_drop, T)
                     d_xin = dX
         return (d_xin, None, None, dW_ih[:3 * H], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * H:], dW_hh[1], db_ih[1], db_hh[1])
 
@@ -280,6 +292,8 @@ class GRULayerBF16WideFn(torch.autograd.Function):
         padded_in, B, T = meta[:3]
         lengths = meta[3] if len(meta) > 3 else None
         drop = meta[4] if len(meta) > 4 else None
+        ctx.in_drop = meta[6] if len(meta) > 6 else None     # see GRULayerBF16Fn
+        ctx.mask_d_out = bool(meta[7]) if len(meta) > 7 else False
         if mask is not None:
             raise _lib.RoomSlamError("GRULayerBF16WideFn: pass dropout as packed bits on the producing layer (meta[4])")
         if w_hh.shape[1] != HW:
@@ -369,7 +383,7 @@ class GRULayerBF16WideFn(torch.autograd.Function):
             wtst = torch.stack([whhT[:, 128 * r: 128 * r + 128].reshape(2, 128, 3 * HW // 16, 2, 8).permute(0, 2, 3, 1, 4)
                                 for r in (0, 1)], 1).to(bf).contiguous()           # [2][2][48 K steps][2][128][8]
             dG = torch.empty(tiles, T + 2, 8 * HC, L.TILE, 8, device=dev, dtype=bf)
-            d_bits, d_scale = ctx.drop if ctx.drop is not None else (None, None)
+            d_bits, d_scale = ctx.drop if (ctx.drop is not None and ctx.mask_d_out) else (None, None)
             with ktime("rec_bwd_wide_kernel", 2.0 * B * T * 2 * 3 * HW * HW):
                 _lib.call("rs_rec_bwd_bf16_wide", _p(d_out), _p(d_h_n), _p(gates), _p(out), _p(wtst), _p(dG), _p(ctx.lengths),
                           _p(d_bits), _p(d_scale), B, T, st)
@@ -416,7 +430,7 @@ class GRULayerBF16WideFn(torch.autograd.Function):
                 wt = L.tile_weight_nt(w_ih_cat.t().contiguous())                   # [Il/128][6H/64][8][128][8]
                 kch = [d * 4 * HC + g * HC + hf * 8 for d in (0, 1) for g in (0, 1, 2) for hf in range(HW // 64)]
                 with ktime("blk_gemm_nt_kernel(dgrad)", 2.0 * tiles * L.TILE * (T + 2) * 6 * HW * Il):
-                    _nt(dG, 8 * HW, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st)
+                    _nt(dG, 8 * HW, kch, wt, Il // 128, dX, Il, 0, None, tiles * (T + 2), st, ctx.in_drop, T)
                 d_xin = dX
         return (d_xin, None, None, dW_ih[:3 * HW], dW_hh[0], db_ih[0], db_hh[0], dW_ih[3 * HW:], dW_hh[1], db_ih[1], db_hh[1])
 

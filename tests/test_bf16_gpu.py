@@ -262,3 +262,25 @@ def test_fused_projection_matches_the_projection_gemm_path(B, T, use_mask, varle
     assert not bad, bad
     _, hn_ref = ref.encode(x, mask, lengths) if not varlen else ref.encode(x, None, lengths)
     assert rel_err(res["1"][0], hn_ref) < RTOL
+
+
+@pytest.mark.parametrize("H,B,T", [(128, 300, 40), (128, 1100, 24), (256, 200, 24)])
+def test_dropout_backward_in_dgrad_epilogue_equals_in_bptt_kernel(H, B, T):
+    """The backward half of inter-layer dropout is applied by the CONSUMING layer (dX (.) mask in the epilogue of its dgrad
+    GEMM, rs_blk_gemm_nt_drop); the BPTT kernel of the producing layer can do the same on the incoming gradient.  Same
+    bits, same weights: the two placements must agree up to the bf16 rounding of dX (rounded after / before the scale)."""
+    from roomslam_b200 import functional as F_, functional_bf16 as FB
+    torch.manual_seed(H + B)
+    dev = RoomSLAM(hidden_size=H, dropout=0.1, precision="bf16").cuda().train()
+    x, tgt = synth.make_sample(B, T, 10, seed=4)
+    bits = [FB.gen_drop_bits(B, T, 2 * H, 0.9, 77, torch.device("cuda"))]
+    grads = []
+    for in_bptt in (False, True):
+        dev.zero_grad()
+        w = dev.encoder.flat_weights()
+        layer_fn = FB.GRULayerBF16Fn if H == 128 else FB.GRULayerBF16WideFn
+        _, h_n = F_.gru_encoder(x.cuda(), bits, 2, w, layer_fn, None, split_weights=False, mask_in_bptt=in_bptt)
+        (h_n ** 2).sum().backward()
+        grads.append([p.grad.clone() for p in dev.encoder.parameters()])
+    for a, b in zip(*grads):
+        assert l2_err(a, b) < 1e-2 and float(b.abs().max()) > 0

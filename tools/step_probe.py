@@ -5,7 +5,7 @@ import torch
 from roomslam_b200 import RoomSLAM, synth, functional as F_
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 torch.manual_seed(0)
-m = RoomSLAM(dropout=0.0, precision="bf16").cuda().train()
+m = RoomSLAM(dropout=float(os.environ.get("RS_PROBE_DROPOUT", "0.0")), precision="bf16").cuda().train()
 x, tgt = synth.make_sample(B, 500, 10, seed=0, device="cuda")
 def step():
     m.zero_grad(); l = m.compute_loss(m(x), tgt)["total"]; l.backward(); return l
