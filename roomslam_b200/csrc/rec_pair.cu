@@ -249,19 +249,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
         }
     } else if (warp == 1 && kProj) {
         // ===================== X tile producer (both CTAs): the layer input of the CTA's 64 rows, one step ahead ==========
-        // 32 pieces of 1 KB (one per 16-byte chunk column), one bulk copy per LANE: issued by one thread they would take
-        // longer to issue than a time step lasts
+        // 32 pieces of 1 KB (one per 16-byte chunk column), all issued by ONE elected thread: under elect.sync ptxas emits the
+        // copies back to back with uniform-register addresses (~3 instructions each).  One copy per lane -- what a lane == 0
+        // guard forces, because it costs an ELECT loop of ~13 instructions per copy -- took 0.9 us per time step (ncu: 27 % of
+        // this warp's samples), and that sits on the path X_{t+1} landed -> projection MMAs -> hidden MMAs of the next step.
         const uint32_t rdy_remote = mapa_cluster(smem_u32(x_rdy), 0);
-        for (int step = 0; step < T; ++step) {
-            const int t = dir ? (T - 1 - step) : step;
-            if (lane == 0) {
+        if (elect_one()) {
+            for (int step = 0; step < T; ++step) {
+                const int t = dir ? (T - 1 - step) : step;
                 if (step > 0) mbar_wait(x_free, (step - 1) & 1);
                 mbar_expect_tx(x_full, 32 * CHUNK_S);
-            }
-            __syncwarp();
-            const uint8_t* src = p.X + ((long long)tile0 * (T + 2) + t + 1) * p.x_block_bytes + rank * 1024;
-            bulk_load(x_s + lane * CHUNK_S, src + (long long)lane * CHUNK_G, 1024, x_full);
-            if (lane == 0) {
+                const uint8_t* src = p.X + ((long long)tile0 * (T + 2) + t + 1) * p.x_block_bytes + rank * 1024;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) bulk_load(x_s + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, x_full);
                 if (step + 3 < T) {                        // L2 prefetch three steps ahead: the copies above then come from L2
                     const int t3 = dir ? (T - 1 - step - 3) : step + 3;
                     l2_prefetch(p.X + ((long long)tile0 * (T + 2) + t3 + 1) * p.x_block_bytes + (long long)(rank * 16) * CHUNK_G, 16 * CHUNK_G);
@@ -269,7 +269,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 mbar_wait(x_full, step & 1);
                 mbar_arrive_cluster(rdy_remote);
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================== L2 prefetcher: this CTA pulls half of the next projection block =====================
@@ -571,16 +570,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 const uint32_t ph = (sidx >> 1) & 1;
                 const int t = dir ? sidx : (T - 1 - sidx);
                 const int t_prev = dir ? t + 1 : t - 1;
-                if (lane == 0) {
+                if (elect_one()) {
                     if (sidx >= 2) mbar_wait(&hp_free[st], ph ^ 1);    // the epilogue of step sidx - 2 is done with this stage
                     mbar_expect_tx(&hp_full[st], HP_BYTES);
-                }
-                __syncwarp();
-                if (lane < 16) {                                       // 16 pieces of 1 KB, one bulk copy per lane
                     const uint8_t* src = p.out + ((long long)tile * (T + 2) + t_prev + 1) * p.out_block_bytes + (long long)(dir * 16) * CHUNK_G + rank * 1024;
-                    bulk_load(hp_s + st * HP_BYTES + lane * CHUNK_S, src + (long long)lane * CHUNK_G, 1024, &hp_full[st]);
-                }
-                if (elect_one()) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)                       // 16 pieces of 1 KB, back to back (see the X tile producer)
+                        bulk_load(hp_s + st * HP_BYTES + c * CHUNK_S, src + (long long)c * CHUNK_G, 1024, &hp_full[st]);
                     if (p.pf_dist > 0 && sidx + p.pf_dist < T) {       // optional L2 prefetch of a later step's gate / d_out blocks
                         const int t2 = dir ? sidx + p.pf_dist : (T - 1 - sidx - p.pf_dist);
                         l2_prefetch(p.gates + (((long long)tile * T + t2) * 2 + dir) * (48LL * CHUNK_G) + (long long)(rank * 24) * CHUNK_G, 24 * CHUNK_G);
