@@ -80,11 +80,12 @@ extern "C" int rs_rec_bwd_bf16(const void* d_out, const float* d_h_n, const void
     RS_REQUIRE(gates && out && WhhT && Whh && b_hn && dG && B >= 0 && T >= 0, "rs_rec_bwd_bf16: bad arguments");
     RS_REQUIRE(whh_chunks >= 16 * (split ? 2 : 1), "rs_rec_bwd_bf16: Whh is the forward image (16 hidden chunks, twice with split)");
     RS_REQUIRE(!drop_bits || drop_scale, "rs_rec_bwd_bf16: drop_bits needs drop_scale");
-    // L2 prefetch (RS_PF_DIST_BWD steps ahead) is off by default: at 8192 traces the kernel runs against the HBM roof and
-    // prefetched lines are evicted before use (round 1), at 1024 traces the step is bound by its compute / sync chain, not
-    // by load latency (7.28 ms per training step without, 7.35 ms with distance 2)
+    // L2 prefetch of the gate / d_out blocks RS_PF_DIST_BWD steps ahead (default 1; issued by the thread that also issues the
+    // h_{t-1} tile copies).  Measured once single-thread issue had become cheap (elect.sync): BPTT at 8192 traces 3.14 / 3.30 ms
+    // per layer without, 2.94 / 3.21 with distance 1, 3.11 / 3.53 with 2, 3.43 / 3.94 with 4 (evicted before use); at 1024
+    // traces 1.16 / 1.18 -> 1.13 / 1.14 ms.
     return rs::rec_bwd_pair(d_out, d_h_n, gates, out, WhhT, Whh, whh_chunks, b_hn, dG, lengths, drop_bits, drop_scale, split, B, T,
-                            pf_dist_env("RS_PF_DIST_BWD", 0), stream);
+                            pf_dist_env("RS_PF_DIST_BWD", 1), stream);
 }
 
 extern "C" int rs_pack_x_tm(const float* x, int B, int T, int I, void* out, void* stream_) {
