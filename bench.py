@@ -281,11 +281,8 @@ def invariance_check(world, rank):
     from roomslam_b200 import RoomSLAM, OccupancyHeatmapBaseline, synth
     from roomslam_b200.train_utils import FlatParams
     out = {}
-    # The bf16 path picks its kernels by batch size (from 38 tiles up the input projection of layer 1 is fused into the
-    # recurrence and P is never rounded to bf16): a shard and the concatenated batch would differ by that rounding (6e-4).
-    # The check compares like with like: both sides run the projection-GEMM path.
-    fuse_env = os.environ.get("RS_FUSE_PROJ")
-    os.environ["RS_FUSE_PROJ"] = "0"
+    # Both sides run the default kernels: from 1024 traces per rank up (8192 / N for N <= 8) the shards and the concatenated
+    # batch take the same path (unsplit weights, input projection of layer 1 fused into the recurrence kernel).
     for precision, per_rank, tol in (("fp32", 64, 1e-5), ("bf16", TRAIN_BATCH // world, 1e-4)):
         G = per_rank * world
         x, tgt = synth.make_sample(G, SEQ_LEN, MAX_OBJECTS, seed=4242)
@@ -312,10 +309,6 @@ def invariance_check(world, rank):
             out[f"grad_global_batch_{precision}"] = G
         del model, flat, g
         torch.cuda.empty_cache()
-    if fuse_env is None:
-        os.environ.pop("RS_FUSE_PROJ", None)
-    else:
-        os.environ["RS_FUSE_PROJ"] = fuse_env
     # heatmap: HEATMAP_TRACES in total, shard r = traces [r n, (r+1) n)
     hm = OccupancyHeatmapBaseline()
     n = HEATMAP_TRACES // world

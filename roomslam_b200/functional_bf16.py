@@ -146,12 +146,13 @@ class GRULayerBF16Fn(torch.autograd.Function):
             ws = [t.detach().float().contiguous() for t in (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
             bf = torch.bfloat16
             need_dx = padded_in and ctx.needs_input_grad[0]
-            # deeper layers: from 38 tiles up (the launch no longer fits one wave of CTA pairs and runs against the HBM roof) the
-            # input projection is fused into the recurrence kernel: W_ih resident next to W_hh, no P in HBM, no projection GEMM
-            # (-1.3 ms per step at 8192 traces).  In the latency-bound regime below, the projection GEMM + P path is 2 % faster
-            # (6.74 vs 6.90 ms per step at 1024 traces), and split weights (W_ih hi + lo) would not fit.  RS_FUSE_PROJ=0/1 forces.
+            # deeper layers: the input projection is fused into the recurrence kernel (W_ih resident next to W_hh, no P in HBM,
+            # no projection GEMM) whenever the weights are not split into hi + lo pairs (W_ih hi + lo would not fit).  Since the
+            # X tile copies are issued by one elected thread the fused kernel is within 6 % of the plain one per time step, and
+            # the projection launch it replaces costs more than that at every batch size (training step at 1024 / 2048 / 4096 /
+            # 8192 traces: 5.85 -> 5.72, 6.83 -> 6.52, 9.55 -> 8.93, 19.6 -> 18.3 ms).  RS_FUSE_PROJ=0/1 forces.
             fuse_env = os.environ.get("RS_FUSE_PROJ")
-            fuse_proj = padded_in and not split and (fuse_env == "1" if fuse_env in ("0", "1") else tiles * 4 > 148)
+            fuse_proj = padded_in and not split and (fuse_env == "1" if fuse_env in ("0", "1") else True)
             whh_img = torch.empty(2, (H // 8) * (1 + split) + (2 if (not padded_in or fuse_proj) else 0), 3 * H, 8, device=dev, dtype=bf)
             b_hn = torch.empty(2, H, device=dev)
             bias_x = torch.empty(2, 3 * H, device=dev)
