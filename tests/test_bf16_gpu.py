@@ -284,3 +284,24 @@ def test_dropout_backward_in_dgrad_epilogue_equals_in_bptt_kernel(H, B, T):
         grads.append([p.grad.clone() for p in dev.encoder.parameters()])
     for a, b in zip(*grads):
         assert l2_err(a, b) < 1e-2 and float(b.abs().max()) > 0
+
+
+@pytest.mark.parametrize("H,B,T", [(128, 1100, 60), (128, 300, 33), (256, 260, 20)])
+def test_recurrence_is_reproducible(H, B, T):
+    """The forward recurrence has no atomics: repeated runs must give BIT-identical outputs and hidden states.  The weight
+    gradients end in fp32 atomic sums, so they may differ by summation order only (1e-5 relative L2).  A race between the
+    epilogue warps, the issuing thread and the copy producers (arrivals before the last stores, loads issued after the
+    arrival, single-thread tile copies) would show up here long before it moves a 2e-2 tolerance."""
+    torch.manual_seed(H + T)
+    dev = RoomSLAM(hidden_size=H, dropout=0.0, precision="bf16").cuda().train()
+    x, _ = synth.make_sample(B, T, 10, seed=11)
+    runs = []
+    for _ in range(3):
+        dev.zero_grad()
+        out, h_n = dev.encode(x.cuda())
+        (h_n.square().sum() + out.square().sum()).backward()
+        runs.append((out.detach().clone(), h_n.detach().clone(), [p.grad.detach().clone() for p in dev.encoder.parameters()]))
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1])
+        for a, b in zip(r[2], runs[0][2]):
+            assert l2_err(a, b) < 1e-5
