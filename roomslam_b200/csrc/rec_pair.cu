@@ -347,7 +347,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             if (!kFusedX) load_p(pblk, 0);
             mbar_wait(&acc_full[s], step & 1);
             tc_fence_after();
-            uint4 last_o, last_d = make_uint4(0, 0, 0, 0), last_r, last_z, last_n;
+            // first chunk whose global stores wait for the arrival: the last one (deferring both chunks of the one-tile mode
+            // costs 16 more live registers and is 14 % slower)
+            constexpr int kDefer0 = NGRP - 1;
+            constexpr int ND = NGRP - kDefer0;
+            uint4 last_o[ND], last_d[ND], last_r[ND], last_z[ND], last_n[ND];
 #pragma unroll
             for (int grp = 0; grp < NGRP; ++grp) {
                 const int u0 = ub + grp * 8;
@@ -406,7 +410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                 const uint4 so = active ? o0 : make_uint4(0, 0, 0, 0), sd = make_uint4(wd[0], wd[1], wd[2], wd[3]);
                 const uint4 sr = make_uint4(wr[0], wr[1], wr[2], wr[3]), sz = make_uint4(wz[0], wz[1], wz[2], wz[3]);
                 const uint4 sn = make_uint4(wn[0], wn[1], wn[2], wn[3]);
-                if (grp < NGRP - 1) {
+                if (grp < kDefer0) {
                     stg16(o_ptr + (long long)grp * CHUNK_G, so);
                     if (kDrop) stg16(od_ptr + (long long)grp * CHUNK_G, sd);
                     if (gblk) {
@@ -415,7 +419,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
                         stg16(gblk + (long long)(2 * 16 + grp) * CHUNK_G, sn);
                     }   // W_hn h + b_hn is not saved: the backward kernel recomputes it on the tensor core
                 } else {                // the last chunk's global stores wait until after the arrival (below)
-                    last_o = so; last_d = sd; last_r = sr; last_z = sz; last_n = sn;
+                    last_o[grp - kDefer0] = so; last_d[grp - kDefer0] = sd; last_r[grp - kDefer0] = sr; last_z[grp - kDefer0] = sz;
+                    last_n[grp - kDefer0] = sn;
                 }
             }
             if (write_x) *reinterpret_cast<uint4*>(a_row + 16 * CHUNK_S) = xnext;
@@ -426,12 +431,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rec_
             // The MEMBAR inside fence.proxy.async waits for every global store of the thread still in flight (ncu: ~0.2 us of
             // a 2.3 us step).  The stores of the earlier chunks are long acknowledged by then; the last chunk's are issued only
             // now, under the wait for the next MMA.
-            stg16(o_ptr + (long long)(NGRP - 1) * CHUNK_G, last_o);
-            if (kDrop) stg16(od_ptr + (long long)(NGRP - 1) * CHUNK_G, last_d);
-            if (gblk) {
-                stg16(gblk + (long long)(0 * 16 + NGRP - 1) * CHUNK_G, last_r);
-                stg16(gblk + (long long)(1 * 16 + NGRP - 1) * CHUNK_G, last_z);
-                stg16(gblk + (long long)(2 * 16 + NGRP - 1) * CHUNK_G, last_n);
+#pragma unroll
+            for (int g = kDefer0; g < NGRP; ++g) {
+                stg16(o_ptr + (long long)g * CHUNK_G, last_o[g - kDefer0]);
+                if (kDrop) stg16(od_ptr + (long long)g * CHUNK_G, last_d[g - kDefer0]);
+                if (gblk) {
+                    stg16(gblk + (long long)(0 * 16 + g) * CHUNK_G, last_r[g - kDefer0]);
+                    stg16(gblk + (long long)(1 * 16 + g) * CHUNK_G, last_z[g - kDefer0]);
+                    stg16(gblk + (long long)(2 * 16 + g) * CHUNK_G, last_n[g - kDefer0]);
+                }
             }
         }
         if (live) {                     // h_n: the fp32 master state after the last step (kept out of the step loop)
