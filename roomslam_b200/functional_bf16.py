@@ -1,12 +1,12 @@
-"""bf16 tensor-core mode of the GRU encoder: orchestration of the tcgen05 kernels (hidden_size = 128).
+"""bf16 tensor-core mode of the GRU encoder: orchestration of the tcgen05 kernels (hidden_size = 128; 256: GRULayerBF16WideFn).
 
 Per layer:   layer 0: fused K=2 input projection inside the recurrence kernel
-             deeper : P = X W_ih^T + b           rs_blk_gemm_nt   (tcgen05, bulk-copy fed)
-             recurrence forward                  rs_rec_fwd_bf16  (persistent, W_hh resident in shared memory)
-backward:    recurrence backward (BPTT)          rs_rec_bwd_bf16  -> dG (r | z | n | hn gate gradients)
-             dW_hh  = dG[r,z,hn]^T h_{t-/+1}     rs_blk_gemm_tn_acc (time-shifted block pairing)
-             dW_ih  = dG[r,z,n]^T X, bias grads  rs_blk_gemm_tn_acc (ones column)
-             dX     = dG[r,z,n] W_ih             rs_blk_gemm_nt
+             deeper : input projection fused into the recurrence kernel (W_ih resident, X_t bulk-copied one step ahead);
+                      with split (hi + lo) weights below 1024 traces: P = X W_ih^T + b by rs_blk_gemm_nt, then the recurrence
+             recurrence forward                  rs_rec_fwd_bf16  (persistent CTA pairs, W_hh resident in shared memory)
+backward:    recurrence backward (BPTT)          rs_rec_bwd_bf16  -> dG (r | z | n | hn gate gradients); W_hn h recomputed
+             dW_ih, dW_hh, bias gradients        rs_blk_wgrad     (one launch per layer, 12 roles over dG)
+             dX     = dG[r,z,n] W_ih             rs_blk_gemm_nt / rs_blk_gemm_nt_drop (x the dropout mask of the layer input)
 All per-timestep activations stay in the tile-major bf16 layout (roomslam_b200/layout.py); master weights and
 weight gradients are fp32.  Tolerance against the fp32 CPU oracle: 2e-2 relative (BASELINE.json north_star).
 """
