@@ -155,7 +155,8 @@ int rs_blk_gemm_tn_acc(const void* A, int64_t a_cols, const int* a_mchunk, const
  * may be 0), when bias[r] != NULL bias[r][128] += column sums of the same dG columns, and when B2[r] != NULL
  * C2[r][128, 16] += the same dG columns ^T . B2[r]_blk (a 16-column tile-major tensor, e.g. the layer-0 input).
  * All arrays are HOST arrays of length n_roles.  Roles should do equal work per block (they share operands through
- * L2 only while they advance in lockstep). */
+ * L2 only while they advance in lockstep).  With an even n_roles, roles 2 j and 2 j + 1 that name the same dG columns
+ * (a_mchunk) run as a CTA pair: the block is read once and multicast into both CTAs -- order the roles accordingly. */
 int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_block, int n_roles, const int* a_mchunk,
                  const void* const* B, const int64_t* b_cols, const int* b_chunk0, const int* n_cols, const int* b_shift,
                  float* const* C, const int64_t* ldc, float* const* bias, const void* const* B2, float* const* C2,

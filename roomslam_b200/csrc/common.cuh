@@ -321,6 +321,20 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
                  : "memory");
 }
 
+// cta_group::1 commit that arrives on the mbarrier at this shared-memory offset in every CTA of `cta_mask` (cluster ranks)
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in `cta_mask`; each destination CTA's mbarrier (same
+// offset) receives the complete_tx of the bytes written there
+__device__ __forceinline__ void bulk_load_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

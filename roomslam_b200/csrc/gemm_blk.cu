@@ -451,8 +451,16 @@ struct WgParams {
     const uint8_t* ones;                // [2 chunks][128][8] bf16, first column = 1
     WgRole role[WG_MAX_ROLES];
     int n_roles, tiles, T, Tp, splits, blocks_per_split, max_b_bytes;
+    // paired launch (cluster of 2 CTAs = roles 2 j, 2 j + 1 of a split): bit j set = the two roles read the SAME dG block, the
+    // even CTA bulk-copies it once with cluster multicast into both CTAs' stages
+    int paired; unsigned int share_mask;
 };
 
+// Paired mode.  A dG block feeds two roles (its ih role against X, its hh role against h); as single CTAs they move 96 and 64 KB
+// per block, drift apart and miss each other in L2 -- layer 1 read exactly its four shared gate blocks twice (16.7 GB for
+// 12.6 GB of operands, ncu).  As a cluster of two the even CTA's producer loads the block ONCE and multicasts it into both
+// stages; it waits for both CTAs' MMAs to retire before it refills a stage (the odd CTA's tcgen05.commit arrives on both
+// empty barriers), each CTA streams its own B operand.  The shared ring keeps the pair in lockstep by construction.
 __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int stage_bytes = 2 * PIECE_BYTES + p.max_b_bytes + 2 * CHUNK_BYTES;   // A | B | B2 (16 columns)
@@ -466,8 +474,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const uint32_t crank = p.paired ? rs::cluster_ctarank() : 0u;
+    // paired launches run ONE item per CTA (host), so the role of this CTA is fixed: does its pair share the dG block?
+    const bool shared_a = p.paired && ((p.share_mask >> ((static_cast<int>(blockIdx.x) % p.n_roles) >> 1)) & 1u);
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < 2; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], 1); }
+        // shared: the even CTA's stage is free only when BOTH CTAs' MMAs on it retired (its own commit + the odd CTA's).
+        // An unshared pair must NOT cross-signal: its odd CTA is not throttled by the even one and would complete the even
+        // CTA's phases with arrivals of later blocks.
+        for (int s = 0; s < 2; ++s) { rs::mbar_init(&full_bar[s], 1); rs::mbar_init(&empty_bar[s], (shared_a && crank == 0) ? 2 : 1); }
         rs::mbar_init(acc_full, 1);
         rs::mbar_init(ones_full, 1);
         rs::fence_mbar_init();
@@ -475,6 +489,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
     if (warp == 1) rs::tmem_alloc<512>(tmem_slot);
     rs::tc_fence_before();
     __syncthreads();
+    if (p.paired) rs::cluster_sync_all();       // the peer's barriers exist before anything is multicast into them
     rs::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -491,6 +506,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
         const int i0 = split * p.blocks_per_split;
         const int i1 = min(total_blocks, i0 + p.blocks_per_split);
         const int b_bytes = R.n_cols * 256;
+        // shared pair: the even CTA loads the dG block for both; else every CTA loads its own
         if (warp == 0) {
             if (rs::elect_one()) {
                 for (int i = i0; i < i1; ++i) {
@@ -498,7 +514,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
                     rs::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = stages + stage * stage_bytes;
                     rs::mbar_expect_tx(&full_bar[stage], 2 * PIECE_BYTES + b_bytes + (R.B2 ? 2 * CHUNK_BYTES : 0));
-                    rs::bulk_load(sa, p.A + blk * p.a_block_bytes + (long long)R.a_mchunk * CHUNK_BYTES, 2 * PIECE_BYTES, &full_bar[stage]);
+                    const uint8_t* asrc = p.A + blk * p.a_block_bytes + (long long)R.a_mchunk * CHUNK_BYTES;
+                    if (!shared_a) rs::bulk_load(sa, asrc, 2 * PIECE_BYTES, &full_bar[stage]);
+                    else if (crank == 0) rs::bulk_load_mc(sa, asrc, 2 * PIECE_BYTES, &full_bar[stage], 3);
                     if (b_bytes)
                         rs::bulk_load(sa + 2 * PIECE_BYTES, R.B + (blk + R.b_shift) * R.b_block_bytes + (long long)R.b_chunk0 * CHUNK_BYTES,
                                       b_bytes, &full_bar[stage]);
@@ -534,7 +552,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
                             rs::tc_mma_bf16(tmem_base + 272, da, d2, idesc1, (i != i0) || (k != 0));
                         }
                     }
-                    rs::tc_commit(&empty_bar[stage]);
+                    if (shared_a && crank == 1) rs::tc_commit_mc(&empty_bar[stage], 3);   // own stage + the even CTA's
+                    else rs::tc_commit(&empty_bar[stage]);
                     if (i == i1 - 1) rs::tc_commit(acc_full);
                 }
                 __syncwarp();
@@ -575,6 +594,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) blk_wgrad_kernel(const WgParam
     }
     rs::tc_fence_before();
     __syncthreads();
+    if (p.paired) rs::cluster_sync_all();       // the peer's commits / multicast copies target this CTA's shared memory
     if (warp == 1) rs::tmem_dealloc<512>(tmem_base);
 }
 
@@ -734,7 +754,26 @@ extern "C" int rs_blk_wgrad(const void* dG, int64_t a_cols, const void* ones_blo
     const int smem = 2 * (2 * PIECE_BYTES + p.max_b_bytes + 2 * CHUNK_BYTES) + 2 * CHUNK_BYTES + 256;
     RS_CUDA_OK(cudaFuncSetAttribute(blk_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int items = n_roles * p.splits;
-    blk_wgrad_kernel<<<items < num_sms() ? items : num_sms(), NUM_THREADS, smem, stream>>>(p);
+    int grid = items < num_sms() ? items : num_sms();
+    // paired mode: roles 2 j and 2 j + 1 form a cluster; where they name the same dG columns the block is loaded once (multicast)
+    static const bool pair_off = getenv("RS_WGRAD_PAIR") && atoi(getenv("RS_WGRAD_PAIR")) == 0;
+    unsigned int share = 0;
+    if (n_roles % 2 == 0 && !pair_off)
+        for (int r = 0; r < n_roles; r += 2)
+            if (a_mchunk[r] == a_mchunk[r + 1]) share |= 1u << (r / 2);
+    if (share && items <= num_sms()) {          // one item per CTA: the pair's roles are fixed for the whole launch
+        grid &= ~1;
+        p.paired = 1; p.share_mask = share;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        RS_CUDA_OK(cudaLaunchKernelEx(&cfg, blk_wgrad_kernel, p));
+    } else {
+        blk_wgrad_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
+    }
     rs::count_launch();
     RS_CUDA_OK(cudaGetLastError());
     return 0;

@@ -248,15 +248,15 @@ class GRULayerBF16Fn(torch.autograd.Function):
             else:
                 # deeper layers: 12 roles: ih (N = 2H) and hh (N = H) per gate block.  (18 equal-weight N = H roles were
                 # tried to keep the roles in lockstep for L2 sharing: slower, 6.1 ms vs 5.5 ms - more L2->SM traffic.)
+                # Roles 2 j, 2 j + 1 run as a CTA pair; where both name the same dG block (r, z) it is loaded once and
+                # multicast into both CTAs (csrc/gemm_blk.cu, paired mode).
                 dW_ih_buf = torch.zeros(6 * H, Il, device=dev)
                 for d in (0, 1):
                     sh = -1 if d == 0 else 1
-                    for g in (0, 1, 2):                            # r, z, n against the layer input
-                        roles.append((d * 64 + g * 16, saved_in, Il, 0, Il, 0, dW_ih_buf[(d * 3 + g) * H:], Il, sums[d, g],
-                                      None, None))
-                    for gi, g in enumerate((0, 1, 3)):             # r, z, hn against the shifted hidden state
-                        roles.append((d * 64 + g * 16, out, 2 * H, d * 16, H, sh, dW_hh[d, gi * H:], H,
-                                      sums[d, 3] if g == 3 else None, None, None))
+                    ih = lambda g: (d * 64 + g * 16, saved_in, Il, 0, Il, 0, dW_ih_buf[(d * 3 + g) * H:], Il, sums[d, g], None, None)  # noqa: E731
+                    hh = lambda gi, g: (d * 64 + g * 16, out, 2 * H, d * 16, H, sh, dW_hh[d, gi * H:], H,                           # noqa: E731
+                                        sums[d, 3] if g == 3 else None, None, None)
+                    roles += [ih(0), hh(0, 0), ih(1), hh(1, 1), ih(2), hh(2, 3)]   # (r, X) (r, h) | (z, X) (z, h) | (n, X) (hn, h)
                 flops = 2.0 * tiles * L.TILE * T * (6 * H * Il + 6 * H * H + 8 * H * 16)
             with ktime("blk_wgrad_kernel", flops):
                 _wgrad(dG, 8 * H, _ones_block(dev), roles, tiles, T, st)
@@ -401,7 +401,7 @@ class GRULayerBF16WideFn(torch.autograd.Function):
             with ktime("blk_wgrad_kernel", flops):
                 for d in (0, 1):                                 # one launch per direction: <= 18 roles of one 128-row gate block
                     sh = -1 if d == 0 else 1
-                    roles = []
+                    roles, hh_roles = [], []
                     for mb in (0, 1):                            # the two 128-row halves of a 256-row gate block
                         m0 = mb * 128
                         if not padded_in:
@@ -413,15 +413,15 @@ class GRULayerBF16WideFn(torch.autograd.Function):
                             roles.append((d * 4 * HC + 2 * HC + mb * 16, None, 0, 0, 0, 0, None, 0, sums[d, 2, m0:], xa_tm,
                                           dW_ih_buf[(d * 3 + 2) * HW + m0:]))
                         else:
-                            for g in (0, 1, 2):                  # r, z, n against the layer input, 256 columns at a time
-                                for nb in range(Il // 256):
+                            for g in (0, 1, 2):                  # r, z, n against the layer input, 256 columns at a time: the two
+                                for nb in range(Il // 256):      # halves of Il are adjacent roles = one CTA pair sharing its dG block
                                     roles.append((d * 4 * HC + g * HC + mb * 16, saved_in, Il, nb * 32, 256, 0,
                                                   dW_ih_buf[(d * 3 + g) * HW + m0:, nb * 256:], Il, sums[d, g, m0:] if nb == 0 else None,
                                                   None, None))
                             for gi, g in enumerate((0, 1, 3)):   # r, z, hn against the shifted hidden state
-                                roles.append((d * 4 * HC + g * HC + mb * 16, out, 2 * HW, d * HC, HW, sh, dW_hh[d, gi * HW + m0:], HW,
-                                              sums[d, 3, m0:] if g == 3 else None, None, None))
-                    _wgrad(dG, 8 * HW, ones, roles, tiles, T, st)
+                                hh_roles.append((d * 4 * HC + g * HC + mb * 16, out, 2 * HW, d * HC, HW, sh, dW_hh[d, gi * HW + m0:], HW,
+                                                 sums[d, 3, m0:] if g == 3 else None, None, None))
+                    _wgrad(dG, 8 * HW, ones, roles + hh_roles, tiles, T, st)
             db_ih = sums[:, :3].reshape(2, 3 * HW)
             db_hh = torch.cat([sums[:, :2].reshape(2, 2 * HW), sums[:, 3]], 1)
             dW_ih = dW_ih_buf[:, :Il].contiguous() if not padded_in else dW_ih_buf
