@@ -10,7 +10,10 @@ done
 for B in ${AB_SIZES:-1024 8192}; do
   for lib in base new; do
     echo "=== $lib B $B"
-    if [ $lib = base ]; then export RS_LIB=$PWD/roomslam_b200/libroomslam_b200_base.so; else unset RS_LIB; fi
+    if [ $lib = base ]; then
+      [ -f roomslam_b200/libroomslam_b200_base.so ] || { echo "(no roomslam_b200/libroomslam_b200_base.so: copy the library there before a change to A/B against it)"; continue; }
+      export RS_LIB=$PWD/roomslam_b200/libroomslam_b200_base.so
+    else unset RS_LIB; fi
     timeout 300 python tools/step_probe.py $B 2>&1 | tail -9
   done
 done
